@@ -1,0 +1,123 @@
+/* include/pgm_cuda.h -- C-ABI of the B200-native Polya-Gamma hot path.
+ *
+ * Drop-in boundary for zoj613/polyagamma's C API:
+ *     include/pgm_random.h:47-74   pgm_random_polyagamma / _fill / _fill2
+ *     include/pgm_density.h:4-14   pgm_polyagamma_{pdf,cdf,logpdf,logcdf}
+ *
+ * What changes with respect to the reference signatures, and nothing else:
+ *   - `bitgen_t*` is replaced by a counter-based Philox4x32-10 stream named by
+ *     `(uint64_t seed, uint64_t offset)`.  Element i of a call draws only from the private
+ *     stream (seed, offset, first_index + i), so results do not depend on launch shape,
+ *     chunking or on how an index range is sharded over GPUs.
+ *   - data pointers are DEVICE pointers (FP64), unless the function name ends in `_host`;
+ *   - a trailing `void* stream` (a `cudaStream_t`; NULL = default stream).  Device-pointer
+ *     entry points are asynchronous on that stream and never synchronise the host;
+ *   - functions return `int`: 0 on success, a positive `cudaError_t` for CUDA failures,
+ *     PGM_CUDA_EINVAL for bad arguments.  As in the reference, an invalid shape parameter is
+ *     NOT an error: it is encoded in the data (h <= 0 or NaN -> NaN, h = +inf -> +inf;
+ *     src/pgm_random.c:137-155,162-168).
+ *
+ * No torch types, no C++ types.  The library allocates only stream-ordered scratch
+ * (`cudaMallocAsync`) for the method-bucketing pass; every in/out buffer is caller-owned.
+ */
+#ifndef PGM_CUDA_H
+#define PGM_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Same values as the reference's `sampler_t` (include/pgm_random.h:13). */
+typedef enum {
+    PGM_CUDA_GAMMA = 0,
+    PGM_CUDA_DEVROYE = 1,
+    PGM_CUDA_ALTERNATE = 2,
+    PGM_CUDA_SADDLE = 3,
+    PGM_CUDA_HYBRID = 4
+} pgm_cuda_sampler_t;
+
+/* OR into `method` to reproduce the reference's envelope constants bit-for-constant
+ * (src/pgm_alternate.c:90 uses log(sqrt(pi/2)); src/pgm_saddle.c:257,325-326 use +log(xc)).
+ * Default (flag clear) uses the mathematically consistent envelopes. */
+#define PGM_CUDA_REF_COMPAT 0x100
+
+#define PGM_CUDA_EINVAL (-1)
+#define PGM_CUDA_MAX_NDIM 8
+
+/* ---- sampling: replaces include/pgm_random.h ------------------------------------------- */
+
+/* pgm_random_polyagamma (include/pgm_random.h:47-48): one draw, returned on the host
+ * (synchronises `stream`).  Returns NaN if a CUDA call fails. */
+double pgm_cuda_random_polyagamma(uint64_t seed, uint64_t offset, double h, double z, int method);
+
+/* pgm_random_polyagamma_fill (include/pgm_random.h:61-63): n iid draws of PG(h, z). */
+int pgm_cuda_random_polyagamma_fill(uint64_t seed, uint64_t offset, double h, double z,
+                                    int method, size_t n, double* d_out, uint64_t first_index,
+                                    void* stream);
+
+/* pgm_random_polyagamma_fill2 (include/pgm_random.h:72-74): out[i] ~ PG(h[i], z[i]).
+ * d_h, d_z, d_out hold n contiguous doubles. */
+int pgm_cuda_random_polyagamma_fill2(uint64_t seed, uint64_t offset, const double* d_h,
+                                     const double* d_z, int method, size_t n, double* d_out,
+                                     uint64_t first_index, void* stream);
+
+/* fill2 over a broadcast index space (what the reference's NpyIter loop feeds to fill2,
+ * polyagamma/_polyagamma.pyx:213-251), without materialising the broadcast operands:
+ * out is C-contiguous with `shape[0..ndim)`; element strides (in doubles, 0 = broadcast) are
+ * given for h and z.  ndim <= PGM_CUDA_MAX_NDIM.  `shape`/strides are HOST arrays. */
+int pgm_cuda_random_polyagamma_fill2_strided(uint64_t seed, uint64_t offset, const double* d_h,
+                                             const double* d_z, int method, int ndim,
+                                             const int64_t* shape, const int64_t* h_strides,
+                                             const int64_t* z_strides, double* d_out,
+                                             uint64_t first_index, void* stream);
+
+/* Host-buffer form of fill2 (the reference's calling convention: all pointers are host
+ * memory).  h_stride / z_stride are 1 (array of n) or 0 (scalar broadcast).  Copies are
+ * chunked and overlapped with the kernels on internal streams of `device`; pinned (page-locked)
+ * buffers give full PCIe speed.  Blocks until `out` is complete. */
+int pgm_cuda_random_polyagamma_fill2_host(uint64_t seed, uint64_t offset, const double* h,
+                                          int h_stride, const double* z, int z_stride, int method,
+                                          size_t n, double* out, uint64_t first_index, int device);
+
+/* Parameter check of polyagamma/_polyagamma.pyx:411-430 (any h <= 1e-4, or non-integer h when
+ * method is DEVROYE) over n contiguous device doubles.  Synchronises; *result = 1 if any
+ * element is invalid. */
+int pgm_cuda_any_invalid_h(const double* d_h, size_t n, int method, int* result, void* stream);
+
+/* ---- densities: replaces include/pgm_density.h ----------------------------------------- */
+/* Elementwise over n contiguous doubles (the reference's functions are scalar and the Cython
+ * `dispatch` loop calls them once per element, polyagamma/_polyagamma.pyx:433-472). */
+int pgm_cuda_polyagamma_pdf(const double* d_x, const double* d_h, const double* d_z, size_t n,
+                            double* d_out, void* stream);
+int pgm_cuda_polyagamma_cdf(const double* d_x, const double* d_h, const double* d_z, size_t n,
+                            double* d_out, void* stream);
+int pgm_cuda_polyagamma_logpdf(const double* d_x, const double* d_h, const double* d_z, size_t n,
+                               double* d_out, void* stream);
+int pgm_cuda_polyagamma_logcdf(const double* d_x, const double* d_h, const double* d_z, size_t n,
+                               double* d_out, void* stream);
+
+/* Broadcast form: which = 0 pdf, 1 cdf, 2 logpdf, 3 logcdf; out is C-contiguous with
+ * `shape`; strides in doubles (0 = broadcast); shape/strides are HOST arrays. */
+int pgm_cuda_polyagamma_density_strided(int which, const double* d_x, const double* d_h,
+                                        const double* d_z, int ndim, const int64_t* shape,
+                                        const int64_t* x_strides, const int64_t* h_strides,
+                                        const int64_t* z_strides, double* d_out, void* stream);
+
+/* ---- introspection ---------------------------------------------------------------------- */
+/* Number of kernels this library has launched in this process (all threads). */
+uint64_t pgm_cuda_launch_count(void);
+/* "polyagamma_b200 <version> sm_100a" */
+const char* pgm_cuda_version(void);
+/* Method the hybrid sampler picks for (h, z): 0 gamma, 1 devroye, 2 alternate, 3 saddle,
+ * 5 normal approximation (src/pgm_random.c:105-121).  Host-side, no GPU needed. */
+int pgm_cuda_hybrid_select(double h, double z);
+/* The Philox call key derived from (seed, offset); host-side, no GPU needed. */
+void pgm_cuda_call_key(uint64_t seed, uint64_t offset, uint32_t key[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGM_CUDA_H */

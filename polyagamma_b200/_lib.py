@@ -1,0 +1,102 @@
+"""ctypes binding of ``libpgm_cuda.so`` (the C-ABI declared in ``include/pgm_cuda.h``).
+
+There is no CPU fallback anywhere in this package: if the CUDA library has not been built the
+import of any compute entry point raises, loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgm_cuda.so")
+
+# include/pgm_cuda.h: pgm_cuda_sampler_t (same values as the reference's sampler_t,
+# include/pgm_random.h:13)
+GAMMA, DEVROYE, ALTERNATE, SADDLE, HYBRID = range(5)
+REF_COMPAT = 0x100
+EINVAL = -1
+
+# Every symbol include/pgm_cuda.h declares; tests check the library exports all of them.
+EXPORTS = (
+    "pgm_cuda_random_polyagamma",
+    "pgm_cuda_random_polyagamma_fill",
+    "pgm_cuda_random_polyagamma_fill2",
+    "pgm_cuda_random_polyagamma_fill2_strided",
+    "pgm_cuda_random_polyagamma_fill2_host",
+    "pgm_cuda_any_invalid_h",
+    "pgm_cuda_polyagamma_pdf",
+    "pgm_cuda_polyagamma_cdf",
+    "pgm_cuda_polyagamma_logpdf",
+    "pgm_cuda_polyagamma_logcdf",
+    "pgm_cuda_polyagamma_density_strided",
+    "pgm_cuda_launch_count",
+    "pgm_cuda_version",
+    "pgm_cuda_hybrid_select",
+    "pgm_cuda_call_key",
+)
+
+_lib = None
+
+
+class ExtensionMissing(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load libpgm_cuda.so (once) and declare its prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ExtensionMissing(
+            f"polyagamma_b200: {LIB_PATH} is missing and there is no CPU fallback. Build it with "
+            "`make -C polyagamma_b200/csrc` or `python -c 'import __graft_entry__ as g; g.build()'`.")
+    L = ctypes.CDLL(LIB_PATH)
+    d, vp, sz, u64, i = ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_int
+    p64 = ctypes.POINTER(ctypes.c_int64)
+    L.pgm_cuda_random_polyagamma.restype = d
+    L.pgm_cuda_random_polyagamma.argtypes = [u64, u64, d, d, i]
+    L.pgm_cuda_random_polyagamma_fill.restype = i
+    L.pgm_cuda_random_polyagamma_fill.argtypes = [u64, u64, d, d, i, sz, vp, u64, vp]
+    L.pgm_cuda_random_polyagamma_fill2.restype = i
+    L.pgm_cuda_random_polyagamma_fill2.argtypes = [u64, u64, vp, vp, i, sz, vp, u64, vp]
+    L.pgm_cuda_random_polyagamma_fill2_strided.restype = i
+    L.pgm_cuda_random_polyagamma_fill2_strided.argtypes = [u64, u64, vp, vp, i, i, p64, p64, p64, vp, u64, vp]
+    L.pgm_cuda_random_polyagamma_fill2_host.restype = i
+    L.pgm_cuda_random_polyagamma_fill2_host.argtypes = [u64, u64, vp, i, vp, i, i, sz, vp, u64, i]
+    L.pgm_cuda_any_invalid_h.restype = i
+    L.pgm_cuda_any_invalid_h.argtypes = [vp, sz, i, ctypes.POINTER(ctypes.c_int), vp]
+    for name in ("pdf", "cdf", "logpdf", "logcdf"):
+        f = getattr(L, "pgm_cuda_polyagamma_" + name)
+        f.restype = i
+        f.argtypes = [vp, vp, vp, sz, vp, vp]
+    L.pgm_cuda_polyagamma_density_strided.restype = i
+    L.pgm_cuda_polyagamma_density_strided.argtypes = [i, vp, vp, vp, i, p64, p64, p64, p64, vp, vp]
+    L.pgm_cuda_launch_count.restype = u64
+    L.pgm_cuda_launch_count.argtypes = []
+    L.pgm_cuda_version.restype = ctypes.c_char_p
+    L.pgm_cuda_version.argtypes = []
+    L.pgm_cuda_hybrid_select.restype = i
+    L.pgm_cuda_hybrid_select.argtypes = [d, d]
+    L.pgm_cuda_call_key.restype = None
+    L.pgm_cuda_call_key.argtypes = [u64, u64, ctypes.POINTER(ctypes.c_uint32)]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    if rc == EINVAL:
+        raise ValueError(f"{what}: invalid argument")
+    raise RuntimeError(f"{what}: CUDA error {rc}")
+
+
+def int64_array(values):
+    arr = (ctypes.c_int64 * max(len(values), 1))(*[int(v) for v in values])
+    return arr
+
+
+def launch_count() -> int:
+    return int(lib().pgm_cuda_launch_count())

@@ -1,0 +1,52 @@
+// pgm_internal.h -- host-side glue shared by the translation units of libpgm_cuda.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "pgm_device.cuh"
+
+namespace pgm {
+
+constexpr int kMaxNdim = 8;
+
+// Broadcast index space: ndim == 0 means "linear" (operands are scalar or contiguous).
+struct Bcast {
+    int ndim;
+    int64_t shape[kMaxNdim];
+    int64_t hs[kMaxNdim];  // element strides of the 2nd operand (h)
+    int64_t zs[kMaxNdim];  // element strides of the 3rd operand (z)
+    int64_t xs[kMaxNdim];  // element strides of the 1st operand (x; densities only)
+};
+
+struct FillArgs {
+    PhiloxKey key;
+    const double* h;   // nullptr: use h_scalar
+    const double* z;   // nullptr: use z_scalar
+    double h_scalar, z_scalar;
+    int64_t h_stride, z_stride;  // linear mode: 1 (array) or 0 (one-element array)
+    double* out;
+    uint64_t first_index;  // Philox index of out[0]
+    uint64_t base;         // first element of the current chunk
+    int compat;
+    Bcast bc;
+};
+
+struct DensityArgs {
+    const double* x;
+    const double* h;
+    const double* z;
+    double* out;
+    Bcast bc;
+};
+
+int launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s);
+int launch_check_h(const double* d_h, size_t n, int devroye, int* d_flag, cudaStream_t s);
+int launch_density(int which, DensityArgs a, uint64_t n, cudaStream_t s);
+uint64_t launch_count();
+void count_launch(uint64_t n);
+
+}  // namespace pgm

@@ -1,0 +1,482 @@
+// pgm_sampler.cu -- the batched Polya-Gamma fill on sm_100a.
+//
+// Replaces src/pgm_random.c:144-180 (pgm_random_polyagamma / _fill / _fill2 and the hybrid
+// dispatch).  Pipeline for one chunk of the output index range:
+//
+//   hybrid:   classify_kernel   method id per element (+ NaN/inf for invalid h), per-block
+//                               histograms
+//             scan_kernel       exclusive scan of the histograms -> per-method list bases
+//             scatter_kernel    ascending per-method element lists (one u32 per element)
+//             per method        persistent_kernel<M> / dense_kernel over that method's list
+//   explicit: persistent_kernel<M> / dense_kernel over the identity list
+//
+// persistent_kernel: every lane owns one element at a time and advances it by ONE proposal
+// attempt per loop trip (pgm_methods.cuh); lanes whose element completed are retired and
+// refilled from a per-bucket work counter, found with __ballot_sync/__popc, so a warp never
+// idles on another lane's rejection loop.  Nothing here synchronises the host.
+#include "pgm_internal.h"
+#include "pgm_methods.cuh"
+
+namespace pgm {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t launch_count() { return g_launches.load(); }
+void count_launch(uint64_t n) { g_launches.fetch_add(n); }
+
+// ---------------------------------------------------------------------------------------
+// operand addressing: scalar / contiguous / broadcast-strided
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void
+load_hz(const FillArgs& a, uint64_t g, double& h, double& z)
+{
+    if (a.bc.ndim == 0) {
+        h = a.h ? a.h[g * a.h_stride] : a.h_scalar;
+        z = a.z ? a.z[g * a.z_stride] : a.z_scalar;
+        return;
+    }
+    int64_t oh = 0, oz = 0;
+    uint64_t rem = g;
+    for (int d = a.bc.ndim - 1; d >= 0; --d) {
+        uint64_t q = rem / (uint64_t)a.bc.shape[d];
+        int64_t i = (int64_t)(rem - q * (uint64_t)a.bc.shape[d]);
+        oh += i * a.bc.hs[d];
+        oz += i * a.bc.zs[d];
+        rem = q;
+    }
+    h = a.h[oh];
+    z = a.z[oz];
+}
+
+// nan_or_inf (src/pgm_random.c:137-141); true if h is not a valid shape
+__device__ __forceinline__ bool
+invalid_h(double h, double& value)
+{
+    if (!(h > 0.0)) {
+        value = nan("");
+        return true;
+    }
+    if (isinf(h)) {
+        value = INFINITY;
+        return true;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// bucketing pre-pass (hybrid)
+// ---------------------------------------------------------------------------------------
+constexpr int kBucketThreads = 256;
+constexpr int kBucketItems = 8;
+constexpr int kBucketTile = kBucketThreads * kBucketItems;  // elements per block
+constexpr int kNumBuckets = 4;                              // devroye, alternate, saddle, normal
+constexpr uint8_t kBucketNone = 255;
+
+__device__ __forceinline__ uint8_t
+bucket_of(int method)
+{
+    // kDevroye=1 -> 0, kAlternate=2 -> 1, kSaddle=3 -> 2, kNormal=5 -> 3
+    return method == kNormal ? 3 : (uint8_t)(method - 1);
+}
+
+// Thread t of warp w in block b owns elements  b*Tile + w*256 + k*32 + lane, k = 0..7.
+__global__ void __launch_bounds__(kBucketThreads)
+classify_kernel(FillArgs a, uint32_t n, uint8_t* __restrict__ meth, uint32_t* __restrict__ block_counts)
+{
+    __shared__ uint32_t s_cnt[kNumBuckets];
+    if (threadIdx.x < kNumBuckets) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wbase = blockIdx.x * kBucketTile + warp * (32 * kBucketItems);
+    uint32_t cnt[kNumBuckets] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < kBucketItems; ++k) {
+        uint32_t e = wbase + k * 32 + lane;
+        uint8_t b = kBucketNone;
+        if (e < n) {
+            double h, z, bad;
+            load_hz(a, a.base + e, h, z);
+            if (invalid_h(h, bad)) {
+                a.out[a.base + e] = bad;
+            }
+            else {
+                b = bucket_of(hybrid_select(h, z));
+            }
+            meth[e] = b;
+        }
+#pragma unroll
+        for (int q = 0; q < kNumBuckets; ++q) {
+            cnt[q] += __popc(__ballot_sync(0xffffffffu, b == q));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < kNumBuckets; ++q) atomicAdd(&s_cnt[q], cnt[q]);
+    }
+    __syncthreads();
+    if (threadIdx.x < kNumBuckets) block_counts[blockIdx.x * kNumBuckets + threadIdx.x] = s_cnt[threadIdx.x];
+}
+
+// One block: exclusive scan over blocks for each bucket; totals and list bases.
+// ctl layout: [0..3] totals, [4..7] bases, [8..11] work counters (zeroed by the host memset)
+__global__ void __launch_bounds__(1024)
+scan_kernel(const uint32_t* __restrict__ block_counts, uint32_t nblocks, uint32_t* __restrict__ block_offsets,
+            uint32_t* __restrict__ ctl)
+{
+    __shared__ uint32_t s_part[1024][kNumBuckets];
+    const uint32_t t = threadIdx.x;
+    const uint32_t per = (nblocks + 1023) / 1024;
+    const uint32_t lo = t * per, hi = min(lo + per, nblocks);
+    uint32_t sum[kNumBuckets] = {0, 0, 0, 0};
+    for (uint32_t b = lo; b < hi; ++b) {
+#pragma unroll
+        for (int q = 0; q < kNumBuckets; ++q) sum[q] += block_counts[b * kNumBuckets + q];
+    }
+#pragma unroll
+    for (int q = 0; q < kNumBuckets; ++q) s_part[t][q] = sum[q];
+    __syncthreads();
+    // Hillis-Steele inclusive scan over the 1024 partials, all four buckets at once
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint32_t v[kNumBuckets];
+#pragma unroll
+        for (int q = 0; q < kNumBuckets; ++q) v[q] = (t >= off) ? s_part[t - off][q] : 0;
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < kNumBuckets; ++q) s_part[t][q] += v[q];
+        __syncthreads();
+    }
+    uint32_t run[kNumBuckets];
+#pragma unroll
+    for (int q = 0; q < kNumBuckets; ++q) run[q] = s_part[t][q] - sum[q];  // exclusive
+    for (uint32_t b = lo; b < hi; ++b) {
+#pragma unroll
+        for (int q = 0; q < kNumBuckets; ++q) {
+            block_offsets[b * kNumBuckets + q] = run[q];
+            run[q] += block_counts[b * kNumBuckets + q];
+        }
+    }
+    if (t == 1023) {
+        uint32_t base = 0;
+#pragma unroll
+        for (int q = 0; q < kNumBuckets; ++q) {
+            ctl[q] = s_part[1023][q];
+            ctl[4 + q] = base;
+            base += s_part[1023][q];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBucketThreads)
+scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __restrict__ block_offsets,
+               const uint32_t* __restrict__ ctl, uint32_t* __restrict__ list)
+{
+    __shared__ uint32_t s_warp[kBucketThreads / 32][kNumBuckets];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wbase = blockIdx.x * kBucketTile + warp * (32 * kBucketItems);
+    uint8_t m[kBucketItems];
+    uint32_t cnt[kNumBuckets] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < kBucketItems; ++k) {
+        uint32_t e = wbase + k * 32 + lane;
+        m[k] = (e < n) ? meth[e] : kBucketNone;
+#pragma unroll
+        for (int q = 0; q < kNumBuckets; ++q) cnt[q] += __popc(__ballot_sync(0xffffffffu, m[k] == q));
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < kNumBuckets; ++q) s_warp[warp][q] = cnt[q];
+    }
+    __syncthreads();
+    uint32_t off[kNumBuckets];
+#pragma unroll
+    for (int q = 0; q < kNumBuckets; ++q) {
+        uint32_t o = ctl[4 + q] + block_offsets[blockIdx.x * kNumBuckets + q];
+        for (uint32_t w = 0; w < warp; ++w) o += s_warp[w][q];
+        off[q] = o;
+    }
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int k = 0; k < kBucketItems; ++k) {
+        uint32_t e = wbase + k * 32 + lane;
+#pragma unroll
+        for (int q = 0; q < kNumBuckets; ++q) {
+            uint32_t mask = __ballot_sync(0xffffffffu, m[k] == q);
+            if (m[k] == q) list[off[q] + __popc(mask & lt)] = e;
+            off[q] += __popc(mask);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// persistent rejection-sampling kernel
+// ---------------------------------------------------------------------------------------
+constexpr int kPersistThreads = 256;
+constexpr uint32_t kWorkBatch = 64;  // elements a warp reserves per atomic
+
+template <class M>
+__global__ void __launch_bounds__(kPersistThreads)
+persistent_kernel(FillArgs a, const uint32_t* __restrict__ list, const uint32_t* __restrict__ ctl, int bucket,
+                  uint32_t count_imm, uint32_t* __restrict__ counter)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    // hybrid: this bucket's count and list base were written by scan_kernel
+    const uint32_t count = ctl ? ctl[bucket] : count_imm;
+    if (ctl) list += ctl[4 + bucket];
+    const bool compat = a.compat != 0;
+
+    typename M::Par par;
+    typename M::State st;
+    Rng rng;
+    uint64_t g = 0;
+    bool active = false;
+    uint32_t wnext = 0, wend = 0;  // warp-uniform reserved range of list positions
+    bool exhausted = (count == 0);
+
+    for (;;) {
+        uint32_t need = __ballot_sync(0xffffffffu, !active);
+        if (need != 0 && !(exhausted && wnext == wend)) {
+            if (wnext == wend) {
+                uint32_t b = 0;
+                if (lane == 0) b = atomicAdd(counter, kWorkBatch);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                if (b >= count) {
+                    exhausted = true;
+                }
+                else {
+                    wnext = b;
+                    wend = min(b + kWorkBatch, count);
+                }
+            }
+            if (wnext < wend) {
+                uint32_t pos = wnext + __popc(need & lt);
+                if (!active && pos < wend) {
+                    uint32_t e = list ? list[pos] : pos;
+                    g = a.base + e;
+                    double h, z, bad;
+                    load_hz(a, g, h, z);
+                    if (invalid_h(h, bad)) {
+                        a.out[g] = bad;
+                    }
+                    else {
+                        M::setup(par, h, z, compat);
+                        M::begin(par, st, h, z, compat);
+                        if (M::empty(st)) {
+                            a.out[g] = 0.0;
+                        }
+                        else {
+                            rng.init(a.key, a.first_index + g);
+                            active = true;
+                        }
+                    }
+                }
+                wnext = min(wnext + (uint32_t)__popc(need), wend);
+            }
+        }
+        if (active) {
+            if (M::step(par, st, rng, compat)) {
+                a.out[g] = st.acc;
+                active = false;
+            }
+        }
+        if (exhausted && wnext == wend && !__any_sync(0xffffffffu, active)) break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// dense kernels: one pass, no outer rejection loop (normal approximation, gamma convolution)
+// ---------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256)
+dense_kernel(FillArgs a, const uint32_t* __restrict__ list, const uint32_t* __restrict__ ctl, int bucket,
+             uint32_t count_imm)
+{
+    const uint32_t count = ctl ? ctl[bucket] : count_imm;
+    if (ctl) list += ctl[4 + bucket];
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < count; pos += gridDim.x * blockDim.x) {
+        uint32_t e = list ? list[pos] : pos;
+        uint64_t g = a.base + e;
+        double h, z, bad;
+        load_hz(a, g, h, z);
+        if (invalid_h(h, bad)) {
+            a.out[g] = bad;
+            continue;
+        }
+        Rng rng;
+        rng.init(a.key, a.first_index + g);
+        a.out[g] = (KIND == kNormal) ? normal_approx_sample(rng, h, z) : gamma_conv_sample(rng, h, z);
+    }
+}
+
+// any_nonpositive (polyagamma/_polyagamma.pyx:411-430)
+__global__ void
+check_h_kernel(const double* __restrict__ h, size_t n, int devroye, int* __restrict__ flag)
+{
+    bool bad = false;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double v = h[i];
+        if (v <= 1e-4 || (devroye && v != floor(v))) bad = true;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// host side: launch plan
+// ---------------------------------------------------------------------------------------
+struct DeviceInfo {
+    int sms = 0;
+    int blocks_per_sm[4] = {0, 0, 0, 0};  // devroye, alternate, saddle persistent kernels
+};
+
+static DeviceInfo
+device_info()
+{
+    static DeviceInfo cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    DeviceInfo& d = cache[dev & 63];
+    if (d.sms == 0) {
+        cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[0], persistent_kernel<Devroye>, kPersistThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[1], persistent_kernel<Alternate>, kPersistThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[2], persistent_kernel<Saddle>, kPersistThreads, 0);
+        for (int i = 0; i < 3; ++i) {
+            if (d.blocks_per_sm[i] < 1) d.blocks_per_sm[i] = 1;
+        }
+        // stream-ordered scratch: keep freed blocks cached in the pool instead of returning
+        // them to the OS at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
+    return d;
+}
+
+static inline uint32_t
+persistent_grid(const DeviceInfo& d, int which, uint64_t count_hint)
+{
+    uint64_t full = (uint64_t)d.sms * d.blocks_per_sm[which];
+    uint64_t need = (count_hint + kPersistThreads - 1) / kPersistThreads;
+    if (need < 1) need = 1;
+    return (uint32_t)(need < full ? need : full);
+}
+
+template <class M>
+static void
+launch_persistent(const DeviceInfo& d, int which, const FillArgs& a, const uint32_t* list, const uint32_t* ctl,
+                  int bucket, uint32_t count_imm, uint64_t count_hint, uint32_t* counter, cudaStream_t s)
+{
+    persistent_kernel<M><<<persistent_grid(d, which, count_hint), kPersistThreads, 0, s>>>(a, list, ctl, bucket,
+                                                                                          count_imm, counter);
+    count_launch(1);
+}
+
+template <int KIND>
+static void
+launch_dense(const DeviceInfo& d, const FillArgs& a, const uint32_t* list, const uint32_t* ctl, int bucket,
+             uint32_t count_imm, uint64_t count_hint, cudaStream_t s)
+{
+    uint64_t need = (count_hint + 255) / 256;
+    uint64_t full = (uint64_t)d.sms * 8;
+    if (need < 1) need = 1;
+    dense_kernel<KIND><<<(uint32_t)(need < full ? need : full), 256, 0, s>>>(a, list, ctl, bucket, count_imm);
+    count_launch(1);
+}
+
+// Elements per pass through the pipeline.  Bounds the scratch (5 B/element + histograms)
+// and keeps list indices in 32 bits.
+constexpr uint64_t kChunk = 1ull << 26;
+
+int
+launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
+{
+    if (n == 0) return 0;
+    const int m = method & 0xff;
+    a.compat = (method & 0x100) ? 1 : 0;
+    if (m < kGamma || m > kHybrid) return -1;
+    DeviceInfo d = device_info();
+    cudaError_t err;
+
+    const bool scalar_params = (a.h == nullptr && a.z == nullptr && a.bc.ndim == 0);
+    int eff = m;
+    if (m == kHybrid && scalar_params) {
+        // src/pgm_random.c:105-121 applied once; invalid h is handled per element by every kernel
+        eff = (a.h_scalar > 0.0 && !isinf(a.h_scalar)) ? hybrid_select(a.h_scalar, a.z_scalar) : kDevroye;
+    }
+
+    if (eff != kHybrid) {
+        uint32_t* counter = nullptr;
+        const uint64_t nchunks = (n + kChunk - 1) / kChunk;
+        const bool persistent = (eff == kDevroye || eff == kAlternate || eff == kSaddle);
+        if (persistent) {
+            if ((err = cudaMallocAsync(&counter, nchunks * sizeof(uint32_t), s)) != cudaSuccess) return (int)err;
+            if ((err = cudaMemsetAsync(counter, 0, nchunks * sizeof(uint32_t), s)) != cudaSuccess) return (int)err;
+        }
+        const uint64_t base0 = a.base;
+        for (uint64_t c = 0; c < nchunks; ++c) {
+            uint64_t off = c * kChunk;
+            uint32_t cn = (uint32_t)((n - off) < kChunk ? (n - off) : kChunk);
+            a.base = base0 + off;
+            switch (eff) {
+                case kDevroye: launch_persistent<Devroye>(d, 0, a, nullptr, nullptr, 0, cn, cn, counter + c, s); break;
+                case kAlternate: launch_persistent<Alternate>(d, 1, a, nullptr, nullptr, 0, cn, cn, counter + c, s); break;
+                case kSaddle: launch_persistent<Saddle>(d, 2, a, nullptr, nullptr, 0, cn, cn, counter + c, s); break;
+                case kNormal: launch_dense<kNormal>(d, a, nullptr, nullptr, 0, cn, cn, s); break;
+                default: launch_dense<kGamma>(d, a, nullptr, nullptr, 0, cn, cn, s); break;
+            }
+        }
+        if (counter) cudaFreeAsync(counter, s);
+        return (int)cudaGetLastError();
+    }
+
+    // hybrid with per-element parameters: bucket by method, then one launch per method
+    const uint64_t cmax = n < kChunk ? n : kChunk;
+    const uint32_t nblocks_max = (uint32_t)((cmax + kBucketTile - 1) / kBucketTile);
+    const size_t list_bytes = ((cmax * sizeof(uint32_t)) + 255) & ~size_t(255);
+    const size_t meth_bytes = (cmax + 255) & ~size_t(255);
+    const size_t hist_bytes = (((size_t)nblocks_max * kNumBuckets * sizeof(uint32_t)) + 255) & ~size_t(255);
+    const size_t ctl_bytes = 256;
+    char* ws = nullptr;
+    if ((err = cudaMallocAsync(&ws, list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes, s)) != cudaSuccess) {
+        return (int)err;
+    }
+    uint32_t* list = (uint32_t*)ws;
+    uint8_t* meth = (uint8_t*)(ws + list_bytes);
+    uint32_t* block_counts = (uint32_t*)(ws + list_bytes + meth_bytes);
+    uint32_t* block_offsets = (uint32_t*)(ws + list_bytes + meth_bytes + hist_bytes);
+    uint32_t* ctl = (uint32_t*)(ws + list_bytes + meth_bytes + 2 * hist_bytes);
+
+    const uint64_t base0 = a.base;
+    for (uint64_t off = 0; off < n; off += kChunk) {
+        uint32_t cn = (uint32_t)((n - off) < kChunk ? (n - off) : kChunk);
+        uint32_t nblocks = (cn + kBucketTile - 1) / kBucketTile;
+        a.base = base0 + off;
+        cudaMemsetAsync(ctl, 0, ctl_bytes, s);
+        classify_kernel<<<nblocks, kBucketThreads, 0, s>>>(a, cn, meth, block_counts);
+        scan_kernel<<<1, 1024, 0, s>>>(block_counts, nblocks, block_offsets, ctl);
+        scatter_kernel<<<nblocks, kBucketThreads, 0, s>>>(meth, cn, block_offsets, ctl, list);
+        count_launch(3);
+        // ctl[q] = count and ctl[4+q] = list base of bucket q stay on the device: the method
+        // kernels read them there, so the host never waits for the histogram.
+        launch_persistent<Devroye>(d, 0, a, list, ctl, 0, 0, cn, ctl + 8, s);
+        launch_persistent<Alternate>(d, 1, a, list, ctl, 1, 0, cn, ctl + 9, s);
+        launch_persistent<Saddle>(d, 2, a, list, ctl, 2, 0, cn, ctl + 10, s);
+        launch_dense<kNormal>(d, a, list, ctl, 3, 0, cn, s);
+    }
+    cudaFreeAsync(ws, s);
+    return (int)cudaGetLastError();
+}
+
+int
+launch_check_h(const double* d_h, size_t n, int devroye, int* d_flag, cudaStream_t s)
+{
+    if (n == 0) return 0;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    check_h_kernel<<<(uint32_t)blocks, 256, 0, s>>>(d_h, n, devroye, d_flag);
+    count_launch(1);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pgm
