@@ -82,6 +82,10 @@ int pgm_cuda_random_polyagamma_fill2_host(uint64_t seed, uint64_t offset, const 
                                           int h_stride, const double* z, int z_stride, int method,
                                           size_t n, double* out, uint64_t first_index, int device);
 
+/* Device time (CUDA events, first copy queued -> last copy done) of this process's most recent
+ * pgm_cuda_random_polyagamma_fill2_host call, in milliseconds. */
+double pgm_cuda_last_host_fill_ms(void);
+
 /* Parameter check of polyagamma/_polyagamma.pyx:411-430 (any h <= 1e-4, or non-integer h when
  * method is DEVROYE) over n contiguous device doubles.  Synchronises; *result = 1 if any
  * element is invalid. */
@@ -109,6 +113,17 @@ int pgm_cuda_polyagamma_density_strided(int which, const double* d_x, const doub
 /* ---- introspection ---------------------------------------------------------------------- */
 /* Number of kernels this library has launched in this process (all threads). */
 uint64_t pgm_cuda_launch_count(void);
+/* Per-kernel device time, for roofline accounting.  Between _begin and _end every kernel this
+ * library launches is bracketed by CUDA events on its own stream; _end synchronises those
+ * events and returns, per kernel kind, the summed milliseconds and the launch count.
+ * Kinds: 0 classify, 1 scan, 2 scatter, 3 devroye, 4 alternate, 5 saddle, 6 normal,
+ * 7 gamma, 8 density.  `cap` = length of both output arrays (>= 9). */
+#define PGM_CUDA_NUM_KERNEL_KINDS 9
+void pgm_cuda_profile_begin(void);
+int pgm_cuda_profile_end(double* ms, uint64_t* launches, int cap);
+/* FP64 (DFMA) peak of the current device in TFLOP/s, measured by a register-resident FMA
+ * microbenchmark: the denominator of the FP64 roofline.  Synchronises `stream`. */
+int pgm_cuda_fp64_peak_tflops(double* tflops, void* stream);
 /* "polyagamma_b200 <version> sm_100a" */
 const char* pgm_cuda_version(void);
 /* Method the hybrid sampler picks for (h, z): 0 gamma, 1 devroye, 2 alternate, 3 saddle,

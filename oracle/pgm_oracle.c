@@ -422,6 +422,7 @@ static void
 dev_setup(dev_par* p, double z)
 {
     p->zz = 0.5 * fabs(z);
+    if (!(p->zz > 0.0)) p->zz = 0.0; /* z = NaN is sampled as z = 0 */
     if (p->zz > 0.0) {
         const double a = 0.8838834764831844;  /* 1/sqrt(2T) */
         const double tt = 0.565685424949238;  /* sqrt(T/2) */

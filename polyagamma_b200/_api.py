@@ -136,7 +136,7 @@ def _as_device_tensor(o, device):
     elif hasattr(o, "__dlpack__") and not isinstance(o, np.ndarray):
         t = torch.from_dlpack(o)
     else:
-        t = torch.from_numpy(np.ascontiguousarray(np.asarray(o, dtype=np.float64)))
+        t = torch.from_numpy(np.asarray(o, dtype=np.float64, order="C"))
     return t.to(device=device, dtype=torch.float64)
 
 
@@ -278,10 +278,15 @@ def _host_out_array(out):
 
 
 def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable_checks=False,
-                      random_state=None, device=None, ref_compat=False):
+                      random_state=None, device=None, ref_compat=False, first_index=0):
     """Draw from PG(h, z).  Same contract as the reference's ``random_polyagamma``
-    (``polyagamma/_polyagamma.pyx:22-256``); see the module docstring for the extensions."""
+    (``polyagamma/_polyagamma.pyx:22-256``); see the module docstring for the extensions.
+
+    ``first_index`` is the global index of the first output element: a shard that passes the
+    same ``random_state`` and its own ``first_index`` draws exactly what a single call over the
+    whole index range would draw for those elements (see ``polyagamma_b200.sharding``)."""
     mid = _method_id(method, ref_compat)
+    fi = int(first_index)
     seed, offset = _resolve_random_state(random_state)
     has_size = size is not None
     has_out = out is not None
@@ -297,22 +302,24 @@ def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable
             if any(s < 0 for s in shape):
                 raise ValueError("negative dimensions are not allowed")
             dev = _device_of(device=device)
-            res = _fill_scalar_device(seed, offset, ch, cz, mid, n, dev).reshape(shape)
+            res = _fill_scalar_device(seed, offset, ch, cz, mid, n, dev, fi).reshape(shape)
             return res if device is not None else res.cpu().numpy()
         if has_out:
             if _is_device_array(out):
                 dev = _device_of(out, device=device)
                 ot = _as_device_tensor_view(out, dev)
-                res = _fill_scalar_device(seed, offset, ch, cz, mid, ot.numel(), dev)
+                res = _fill_scalar_device(seed, offset, ch, cz, mid, ot.numel(), dev, fi)
                 ot.copy_(res.reshape(ot.shape))
                 return out
             arr = _host_out_array(out)
             dev = _device_of(device=device)
-            res = _fill_scalar_device(seed, offset, ch, cz, mid, arr.size, dev).cpu().numpy()
+            res = _fill_scalar_device(seed, offset, ch, cz, mid, arr.size, dev, fi).cpu().numpy()
             arr[...] = res.reshape(arr.shape)
             return out
         torch = _require_cuda()
         with torch.cuda.device(_device_of(device=device)):
+            if fi:
+                return float(_fill_scalar_device(seed, offset, ch, cz, mid, 1, _device_of(device=device), fi).item())
             return float(_lib.lib().pgm_cuda_random_polyagamma(seed, offset, ch, cz, mid))
 
     # ---- array path (polyagamma/_polyagamma.pyx:195-256) ----
@@ -328,29 +335,29 @@ def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable
             if shape != _shape_from_size(size):
                 raise ValueError("operands could not be broadcast together with remapped shapes "
                                  f"{tuple(ht.shape)} {tuple(zt.shape)} and requested shape {_shape_from_size(size)}")
-            return _fill_arrays_device(seed, offset, ht, zt, shape, mid, dev)
+            return _fill_arrays_device(seed, offset, ht, zt, shape, mid, dev, first_index=fi)
         if has_out:
             if _is_device_array(out):
                 ot = _as_device_tensor_view(out, dev)
                 shape = tuple(ot.shape)
                 torch = _torch()
                 direct = ot.dtype == torch.float64 and ot.is_contiguous()
-                res = _fill_arrays_device(seed, offset, ht, zt, shape, mid, dev, out=ot if direct else None)
+                res = _fill_arrays_device(seed, offset, ht, zt, shape, mid, dev, out=ot if direct else None, first_index=fi)
                 if not direct:
                     ot.copy_(res)
                 return out
             arr = _host_out_array(out)
-            res = _fill_arrays_device(seed, offset, ht, zt, tuple(arr.shape), mid, dev)
+            res = _fill_arrays_device(seed, offset, ht, zt, tuple(arr.shape), mid, dev, first_index=fi)
             arr[...] = res.cpu().numpy()
             return out
         shape = _broadcast_shape(tuple(ht.shape), tuple(zt.shape))
-        return _fill_arrays_device(seed, offset, ht, zt, shape, mid, dev)
+        return _fill_arrays_device(seed, offset, ht, zt, shape, mid, dev, first_index=fi)
 
     # host operands -> host result
-    harr = np.ascontiguousarray(np.asarray(h, dtype=np.float64))
+    harr = np.asarray(h, dtype=np.float64, order="C")
     if not disable_checks and _check_h_host(harr, mid):
         raise ValueError(PARAM_CHECK_ERROR_MSG)
-    zarr = np.ascontiguousarray(np.asarray(z, dtype=np.float64))
+    zarr = np.asarray(z, dtype=np.float64, order="C")
     arr = None
     if has_size:
         want = _shape_from_size(size)
@@ -366,7 +373,7 @@ def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable
                              f"{harr.shape} {zarr.shape} {shape}")
     else:
         shape = _broadcast_shape(harr.shape, zarr.shape)
-    res = _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr)
+    res = _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr, fi)
     if arr is not None:
         if res is not arr:
             arr[...] = res
@@ -384,7 +391,7 @@ def _as_device_tensor_view(o, dev):
     return torch.from_dlpack(o)
 
 
-def _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr=None):
+def _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr=None, first_index=0):
     """Host operands.  When h and z are each a scalar or already of the full output shape the
     pipelined host-buffer entry point is used (copies overlap the kernels); other broadcasts
     upload the un-broadcast operands and read the result back."""
@@ -402,12 +409,12 @@ def _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr=None):
         res = arr if direct else np.empty(shape, dtype=np.float64)
         rc = _lib.lib().pgm_cuda_random_polyagamma_fill2_host(
             seed, offset, harr.ctypes.data, 0 if harr.size == 1 else 1, zarr.ctypes.data,
-            0 if zarr.size == 1 else 1, mid, n, res.ctypes.data, 0, dev.index)
+            0 if zarr.size == 1 else 1, mid, n, res.ctypes.data, first_index, dev.index)
         _lib.check(rc, "pgm_cuda_random_polyagamma_fill2_host")
         return res
     ht = torch.from_numpy(harr).to(dev)
     zt = torch.from_numpy(zarr).to(dev)
-    return _fill_arrays_device(seed, offset, ht, zt, tuple(shape), mid, dev).cpu().numpy()
+    return _fill_arrays_device(seed, offset, ht, zt, tuple(shape), mid, dev, first_index=first_index).cpu().numpy()
 
 
 # ------------------------------------------------------------------------------------------

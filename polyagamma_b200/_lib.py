@@ -24,6 +24,7 @@ EXPORTS = (
     "pgm_cuda_random_polyagamma_fill2",
     "pgm_cuda_random_polyagamma_fill2_strided",
     "pgm_cuda_random_polyagamma_fill2_host",
+    "pgm_cuda_last_host_fill_ms",
     "pgm_cuda_any_invalid_h",
     "pgm_cuda_polyagamma_pdf",
     "pgm_cuda_polyagamma_cdf",
@@ -31,6 +32,9 @@ EXPORTS = (
     "pgm_cuda_polyagamma_logcdf",
     "pgm_cuda_polyagamma_density_strided",
     "pgm_cuda_launch_count",
+    "pgm_cuda_profile_begin",
+    "pgm_cuda_profile_end",
+    "pgm_cuda_fp64_peak_tflops",
     "pgm_cuda_version",
     "pgm_cuda_hybrid_select",
     "pgm_cuda_call_key",
@@ -65,6 +69,8 @@ def lib() -> ctypes.CDLL:
     L.pgm_cuda_random_polyagamma_fill2_strided.argtypes = [u64, u64, vp, vp, i, i, p64, p64, p64, vp, u64, vp]
     L.pgm_cuda_random_polyagamma_fill2_host.restype = i
     L.pgm_cuda_random_polyagamma_fill2_host.argtypes = [u64, u64, vp, i, vp, i, i, sz, vp, u64, i]
+    L.pgm_cuda_last_host_fill_ms.restype = d
+    L.pgm_cuda_last_host_fill_ms.argtypes = []
     L.pgm_cuda_any_invalid_h.restype = i
     L.pgm_cuda_any_invalid_h.argtypes = [vp, sz, i, ctypes.POINTER(ctypes.c_int), vp]
     for name in ("pdf", "cdf", "logpdf", "logcdf"):
@@ -75,6 +81,12 @@ def lib() -> ctypes.CDLL:
     L.pgm_cuda_polyagamma_density_strided.argtypes = [i, vp, vp, vp, i, p64, p64, p64, p64, vp, vp]
     L.pgm_cuda_launch_count.restype = u64
     L.pgm_cuda_launch_count.argtypes = []
+    L.pgm_cuda_profile_begin.restype = None
+    L.pgm_cuda_profile_begin.argtypes = []
+    L.pgm_cuda_profile_end.restype = i
+    L.pgm_cuda_profile_end.argtypes = [ctypes.POINTER(d), ctypes.POINTER(u64), i]
+    L.pgm_cuda_fp64_peak_tflops.restype = i
+    L.pgm_cuda_fp64_peak_tflops.argtypes = [ctypes.POINTER(d), vp]
     L.pgm_cuda_version.restype = ctypes.c_char_p
     L.pgm_cuda_version.argtypes = []
     L.pgm_cuda_hybrid_select.restype = i
@@ -100,3 +112,25 @@ def int64_array(values):
 
 def launch_count() -> int:
     return int(lib().pgm_cuda_launch_count())
+
+
+KERNEL_KINDS = ("classify", "scan", "scatter", "devroye", "alternate", "saddle", "normal", "gamma", "density")
+
+
+def profile_begin() -> None:
+    lib().pgm_cuda_profile_begin()
+
+
+def profile_end() -> dict:
+    """{kind: (milliseconds, launches)} accumulated since profile_begin()."""
+    n = len(KERNEL_KINDS)
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_uint64 * n)()
+    check(lib().pgm_cuda_profile_end(ms, cnt, n), "pgm_cuda_profile_end")
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_KINDS)}
+
+
+def fp64_peak_tflops() -> float:
+    v = ctypes.c_double(0.0)
+    check(lib().pgm_cuda_fp64_peak_tflops(ctypes.byref(v), None), "pgm_cuda_fp64_peak_tflops")
+    return float(v.value)

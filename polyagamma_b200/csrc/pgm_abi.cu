@@ -92,6 +92,26 @@ pgm_cuda_launch_count(void)
     return launch_count();
 }
 
+void
+pgm_cuda_profile_begin(void)
+{
+    profile_begin();
+}
+
+int
+pgm_cuda_profile_end(double* ms, uint64_t* launches, int cap)
+{
+    if (ms == nullptr || launches == nullptr || cap < 0) return PGM_CUDA_EINVAL;
+    return profile_end(ms, launches, cap);
+}
+
+int
+pgm_cuda_fp64_peak_tflops(double* tflops, void* stream)
+{
+    if (tflops == nullptr) return PGM_CUDA_EINVAL;
+    return measure_fp64_peak(tflops, (cudaStream_t)stream);
+}
+
 int
 pgm_cuda_hybrid_select(double h, double z)
 {
@@ -186,6 +206,7 @@ constexpr size_t kHostChunk = size_t(1) << 23;  // elements per ring slot (64 Mi
 
 struct HostRing {
     bool ready = false;
+    cudaEvent_t ev_start, ev_end, ev_join[kHostStreams];
     cudaStream_t streams[kHostStreams];
     double* d_h[kHostStreams];
     double* d_z[kHostStreams];
@@ -193,6 +214,7 @@ struct HostRing {
 };
 HostRing g_rings[64];
 std::mutex g_ring_mutex;
+double g_last_host_fill_ms = 0.0;
 
 int
 ring_init(HostRing& r)
@@ -204,7 +226,10 @@ ring_init(HostRing& r)
         if ((e = cudaMalloc(&r.d_h[i], kHostChunk * sizeof(double))) != cudaSuccess) return (int)e;
         if ((e = cudaMalloc(&r.d_z[i], kHostChunk * sizeof(double))) != cudaSuccess) return (int)e;
         if ((e = cudaMalloc(&r.d_out[i], kHostChunk * sizeof(double))) != cudaSuccess) return (int)e;
+        cudaEventCreateWithFlags(&r.ev_join[i], cudaEventDisableTiming);
     }
+    cudaEventCreate(&r.ev_start);
+    cudaEventCreate(&r.ev_end);
     r.ready = true;
     return 0;
 }
@@ -226,6 +251,10 @@ pgm_cuda_random_polyagamma_fill2_host(uint64_t seed, uint64_t offset, const doub
     int rc = ring_init(r);
     if (rc != 0) return rc;
 
+    // device-side clock of the whole call: start on stream 0 before any copy is queued, end on
+    // stream 0 after it has joined the other ring streams
+    cudaEventRecord(r.ev_start, r.streams[0]);
+    for (int i = 1; i < kHostStreams; ++i) cudaStreamWaitEvent(r.streams[i], r.ev_start, 0);
     size_t c = 0;
     for (size_t off = 0; off < n; off += kHostChunk, ++c) {
         const int slot = (int)(c % kHostStreams);
@@ -256,11 +285,24 @@ pgm_cuda_random_polyagamma_fill2_host(uint64_t seed, uint64_t offset, const doub
             cudaSuccess)
             return (int)e;
     }
+    for (int i = 1; i < kHostStreams; ++i) {
+        cudaEventRecord(r.ev_join[i], r.streams[i]);
+        cudaStreamWaitEvent(r.streams[0], r.ev_join[i], 0);
+    }
+    cudaEventRecord(r.ev_end, r.streams[0]);
     for (int i = 0; i < kHostStreams; ++i) {
         cudaError_t e = cudaStreamSynchronize(r.streams[i]);
         if (e != cudaSuccess) return (int)e;
     }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.ev_start, r.ev_end) == cudaSuccess) g_last_host_fill_ms = ms;
     return 0;
+}
+
+double
+pgm_cuda_last_host_fill_ms(void)
+{
+    return g_last_host_fill_ms;
 }
 
 int

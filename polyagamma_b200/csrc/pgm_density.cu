@@ -228,6 +228,7 @@ launch_density(int which, DensityArgs a, uint64_t n, cudaStream_t s)
     uint64_t need = (n + 255) / 256;
     uint64_t full = (uint64_t)sms * 8;
     uint32_t grid = (uint32_t)(need < full ? need : full);
+    ScopedKernelTimer timer(kKindDensity, s);
     switch (which) {
         case 0: density_kernel<0><<<grid, 256, 0, s>>>(a, n); break;
         case 1: density_kernel<1><<<grid, 256, 0, s>>>(a, n); break;

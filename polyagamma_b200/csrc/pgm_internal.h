@@ -6,6 +6,8 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
+#include <vector>
 
 #include "pgm_device.cuh"
 
@@ -48,5 +50,34 @@ int launch_check_h(const double* d_h, size_t n, int devroye, int* d_flag, cudaSt
 int launch_density(int which, DensityArgs a, uint64_t n, cudaStream_t s);
 uint64_t launch_count();
 void count_launch(uint64_t n);
+int measure_fp64_peak(double* tflops, cudaStream_t s);
+
+// kernel kinds reported by pgm_cuda_profile_end
+enum : int {
+    kKindClassify = 0,
+    kKindScan = 1,
+    kKindScatter = 2,
+    kKindDevroye = 3,
+    kKindAlternate = 4,
+    kKindSaddle = 5,
+    kKindNormal = 6,
+    kKindGamma = 7,
+    kKindDensity = 8,
+    kNumKinds = 9
+};
+
+class ScopedKernelTimer {
+public:
+    ScopedKernelTimer(int kind, cudaStream_t s);
+    ~ScopedKernelTimer();
+
+private:
+    int kind_;
+    cudaStream_t stream_;
+    bool on_;
+    cudaEvent_t e0_, e1_;
+};
+void profile_begin();
+int profile_end(double* ms, uint64_t* launches, int cap);
 
 }  // namespace pgm

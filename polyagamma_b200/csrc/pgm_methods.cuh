@@ -41,6 +41,7 @@ struct Devroye {
     static __device__ __forceinline__ void setup(Par& p, double /*h*/, double z, bool /*compat*/)
     {
         p.zz = 0.5 * fabs(z);
+        if (!(p.zz > 0.0)) p.zz = 0.0;  // z = NaN is sampled as z = 0
         if (p.zz > 0.0) {
             const double a = 0.8838834764831844;  // 1 / sqrt(2T)
             const double tt = 0.565685424949238;  // sqrt(T / 2)

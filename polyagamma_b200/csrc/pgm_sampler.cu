@@ -23,6 +23,72 @@ static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
 void count_launch(uint64_t n) { g_launches.fetch_add(n); }
 
+// Optional per-kernel timing (bench.py's roofline leg): CUDA events recorded on the launching
+// stream around every kernel while profiling is on; read back by profile_end().
+struct TimedLaunch {
+    int kind;
+    cudaEvent_t e0, e1;
+};
+static std::mutex g_prof_mutex;
+static bool g_prof_on = false;
+static std::vector<TimedLaunch> g_prof;
+
+ScopedKernelTimer::ScopedKernelTimer(int kind, cudaStream_t s) : kind_(kind), stream_(s), on_(false)
+{
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (!g_prof_on) return;
+    on_ = true;
+    cudaEventCreate(&e0_);
+    cudaEventCreate(&e1_);
+    cudaEventRecord(e0_, stream_);
+}
+
+ScopedKernelTimer::~ScopedKernelTimer()
+{
+    if (!on_) return;
+    cudaEventRecord(e1_, stream_);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof.push_back(TimedLaunch{kind_, e0_, e1_});
+}
+
+void
+profile_begin()
+{
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    for (auto& t : g_prof) {
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    g_prof.clear();
+    g_prof_on = true;
+}
+
+int
+profile_end(double* ms, uint64_t* launches, int cap)
+{
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof_on = false;
+    for (int i = 0; i < cap; ++i) {
+        ms[i] = 0.0;
+        launches[i] = 0;
+    }
+    int rc = 0;
+    for (auto& t : g_prof) {
+        float f = 0.f;
+        cudaError_t e = cudaEventSynchronize(t.e1);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&f, t.e0, t.e1);
+        if (e != cudaSuccess) rc = (int)e;
+        if (t.kind >= 0 && t.kind < cap) {
+            ms[t.kind] += f;
+            launches[t.kind] += 1;
+        }
+        cudaEventDestroy(t.e0);
+        cudaEventDestroy(t.e1);
+    }
+    g_prof.clear();
+    return rc;
+}
+
 // ---------------------------------------------------------------------------------------
 // operand addressing: scalar / contiguous / broadcast-strided
 // ---------------------------------------------------------------------------------------
@@ -367,6 +433,7 @@ static void
 launch_persistent(const DeviceInfo& d, int which, const FillArgs& a, const uint32_t* list, const uint32_t* ctl,
                   int bucket, uint32_t count_imm, uint64_t count_hint, uint32_t* counter, cudaStream_t s)
 {
+    ScopedKernelTimer timer(kKindDevroye + which, s);
     persistent_kernel<M><<<persistent_grid(d, which, count_hint), kPersistThreads, 0, s>>>(a, list, ctl, bucket,
                                                                                           count_imm, counter);
     count_launch(1);
@@ -380,6 +447,7 @@ launch_dense(const DeviceInfo& d, const FillArgs& a, const uint32_t* list, const
     uint64_t need = (count_hint + 255) / 256;
     uint64_t full = (uint64_t)d.sms * 8;
     if (need < 1) need = 1;
+    ScopedKernelTimer timer(KIND == kNormal ? kKindNormal : kKindGamma, s);
     dense_kernel<KIND><<<(uint32_t)(need < full ? need : full), 256, 0, s>>>(a, list, ctl, bucket, count_imm);
     count_launch(1);
 }
@@ -453,9 +521,18 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         uint32_t nblocks = (cn + kBucketTile - 1) / kBucketTile;
         a.base = base0 + off;
         cudaMemsetAsync(ctl, 0, ctl_bytes, s);
-        classify_kernel<<<nblocks, kBucketThreads, 0, s>>>(a, cn, meth, block_counts);
-        scan_kernel<<<1, 1024, 0, s>>>(block_counts, nblocks, block_offsets, ctl);
-        scatter_kernel<<<nblocks, kBucketThreads, 0, s>>>(meth, cn, block_offsets, ctl, list);
+        {
+            ScopedKernelTimer timer(kKindClassify, s);
+            classify_kernel<<<nblocks, kBucketThreads, 0, s>>>(a, cn, meth, block_counts);
+        }
+        {
+            ScopedKernelTimer timer(kKindScan, s);
+            scan_kernel<<<1, 1024, 0, s>>>(block_counts, nblocks, block_offsets, ctl);
+        }
+        {
+            ScopedKernelTimer timer(kKindScatter, s);
+            scatter_kernel<<<nblocks, kBucketThreads, 0, s>>>(meth, cn, block_offsets, ctl, list);
+        }
         count_launch(3);
         // ctl[q] = count and ctl[4+q] = list base of bucket q stay on the device: the method
         // kernels read them there, so the host never waits for the histogram.
@@ -465,6 +542,59 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         launch_dense<kNormal>(d, a, list, ctl, 3, 0, cn, s);
     }
     cudaFreeAsync(ws, s);
+    return (int)cudaGetLastError();
+}
+
+// DFMA microbenchmark: the FP64 roofline denominator, measured on the box it is quoted on.
+__global__ void __launch_bounds__(256)
+dfma_peak_kernel(double* sink, int iters, double b, double c)
+{
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a0 = fma(a0, b, c);
+            a1 = fma(a1, b, c);
+            a2 = fma(a2, b, c);
+            a3 = fma(a3, b, c);
+            a4 = fma(a4, b, c);
+            a5 = fma(a5, b, c);
+            a6 = fma(a6, b, c);
+            a7 = fma(a7, b, c);
+        }
+    }
+    double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (r == 12345.678) sink[0] = r;
+}
+
+int
+measure_fp64_peak(double* tflops, cudaStream_t s)
+{
+    DeviceInfo d = device_info();
+    double* sink = nullptr;
+    cudaError_t e;
+    if ((e = cudaMallocAsync(&sink, sizeof(double), s)) != cudaSuccess) return (int)e;
+    const int iters = 4096, blocks = d.sms * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, s);
+        dfma_peak_kernel<<<blocks, 256, 0, s>>>(sink, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, s);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    count_launch(4);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFreeAsync(sink, s);
+    double flops = (double)blocks * 256.0 * iters * 64.0 * 2.0;
+    *tflops = flops / (best * 1e-3) / 1e12;
     return (int)cudaGetLastError();
 }
 

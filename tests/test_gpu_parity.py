@@ -1,0 +1,457 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI, against the CPU oracle.
+
+Sampler parity is element-by-element: kernels and oracle consume the same Philox stream per
+element, so outputs agree to rounding except where a 1-ulp libm difference flips an
+accept/reject decision (tolerated fraction: 1e-3; observed: 0).  Density parity is 1e-10
+relative where the alternating series is well conditioned (SURVEY 8-DEFECTS g), as north_star
+asks.  Full-size runs are checked through size-independent properties.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+from conftest import gamma_sum_moments, ks_vs_quantiles, moment_zscores, pg_moments
+
+pytestmark = pytest.mark.gpu
+
+RTOL_STREAM = 1e-9      # per-element agreement with the oracle
+MAX_FLIPPED = 1e-3      # fraction of elements allowed to differ (decision flips)
+RTOL_DENSITY = 1e-10    # north_star: pdf/cdf within 1e-10 relative outside underflow
+
+
+@pytest.fixture(scope="module")
+def pg():
+    import polyagamma_b200 as pg
+
+    return pg
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    return torch
+
+
+def _cuda(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def _frac_agree(got, want):
+    both_nan = np.isnan(got) & np.isnan(want)
+    same_inf = np.isinf(got) & (got == want)
+    with np.errstate(all="ignore"):
+        close = np.abs(got - want) <= RTOL_STREAM * np.abs(want)
+    return float(np.mean(close | both_nan | same_inf))
+
+
+CASES = {
+    "devroye": lambda r, n: (r.integers(1, 6, n).astype(float), r.uniform(-50, 50, n)),
+    "devroye_smallz": lambda r, n: (np.ones(n), r.normal(0, 3, n)),
+    "alternate": lambda r, n: (r.uniform(1, 4, n), r.uniform(-50, 50, n)),
+    "alternate_chunked": lambda r, n: (r.uniform(0.1, 14, n), r.uniform(-6, 6, n)),
+    "saddle": lambda r, n: (r.uniform(10, 100, n), r.uniform(-50, 50, n)),
+    "saddle_small": lambda r, n: (r.uniform(4.1, 12, n), r.uniform(-5, 5, n)),
+    "gamma": lambda r, n: (r.uniform(0.1, 3, n // 10), r.uniform(-50, 50, n // 10)),
+    "hybrid": lambda r, n: (r.uniform(0.1, 200, n), r.uniform(-50, 50, n)),
+    "hybrid_small": lambda r, n: (np.where(r.random(n) < 0.5, r.integers(1, 9, n), r.uniform(0.1, 9, n)),
+                                  r.uniform(-8, 8, n)),
+}
+
+
+@pytest.mark.parametrize("compat", (False, True))
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_fill2_stream_parity(pg, torch, oracle, case, compat):
+    rng = np.random.default_rng(abs(hash(case)) % 2**32)
+    h, z = CASES[case](rng, 20000)
+    z[::17] = 0.0
+    method = None if case.startswith("hybrid") else case.split("_")[0]
+    got = pg.random_polyagamma(_cuda(torch, h), _cuda(torch, z), method=method, random_state=(7, 3),
+                               ref_compat=compat, disable_checks=True).cpu().numpy()
+    want = oracle.fill2(7, 3, h, z, method, ref_compat=compat)
+    assert np.all(np.isfinite(got))
+    assert _frac_agree(got, want) >= 1.0 - MAX_FLIPPED
+
+
+@pytest.mark.parametrize("method,h,z", [("devroye", 1, 0), ("devroye", 3, 2.5), ("alternate", 2.5, 1),
+                                        ("alternate", 7.3, 6), ("saddle", 20, 3), (None, 60, 2),
+                                        (None, 1, 0), (None, 3.3, -2), ("gamma", 1.5, 1)])
+def test_fill_scalar_stream_parity(pg, oracle, method, h, z):
+    n = 20000 if method != "gamma" else 1000
+    got = pg.random_polyagamma(h, z, size=n, method=method, random_state=(9, 0))
+    want = oracle.fill(9, 0, h, z, n, method)
+    assert _frac_agree(got, want) >= 1.0 - MAX_FLIPPED
+
+
+def test_fill_equals_fill2(pg, torch):
+    """Unlike the reference (fill == fill2[::-1], SURVEY 8-DEFECTS h) both entry points give
+    the same element stream."""
+    n = 10000
+    a = pg.random_polyagamma(2.0, 1.5, size=n, random_state=(3, 1), device="cuda")
+    b = pg.random_polyagamma(torch.full((n,), 2.0, dtype=torch.float64, device="cuda"),
+                             torch.full((n,), 1.5, dtype=torch.float64, device="cuda"), random_state=(3, 1))
+    assert torch.equal(a, b)
+
+
+def test_launch_shape_independence(pg, torch):
+    """1/2/4/8-way partitionings (and ragged ones) of the index range are bit-identical."""
+    rng = np.random.default_rng(0)
+    n = 200_003
+    h = _cuda(torch, rng.uniform(0.1, 200, n))
+    z = _cuda(torch, rng.uniform(-50, 50, n))
+    whole = pg.random_polyagamma(h, z, random_state=(77, 2), disable_checks=True)
+    from polyagamma_b200.sharding import shard_range
+
+    for world in (2, 4, 8, 3):
+        parts = []
+        for r in range(world):
+            lo, hi = shard_range(n, r, world)
+            parts.append(pg.random_polyagamma(h[lo:hi], z[lo:hi], random_state=(77, 2), first_index=lo,
+                                              disable_checks=True))
+        assert torch.equal(torch.cat(parts), whole), world
+    assert not torch.equal(pg.random_polyagamma(h, z, random_state=(77, 3), disable_checks=True), whole)
+
+
+def test_chunk_boundary(pg, torch):
+    """The pipeline processes 2^26 elements per pass; results must not see the seam."""
+    n = (1 << 26) + 4096
+    a = pg.random_polyagamma(1.0, 0.7, size=n, random_state=(5, 0), device="cuda")
+    tail = pg.random_polyagamma(1.0, 0.7, size=8192, random_state=(5, 0), device="cuda", first_index=n - 8192)
+    assert torch.equal(a[-8192:], tail)
+    h = torch.rand(n, device="cuda", dtype=torch.float64) * 100 + 0.1
+    z = torch.rand(n, device="cuda", dtype=torch.float64) * 20 - 10
+    b = pg.random_polyagamma(h, z, random_state=(5, 1), disable_checks=True)
+    tail = pg.random_polyagamma(h[-8192:], z[-8192:], random_state=(5, 1), first_index=n - 8192, disable_checks=True)
+    assert torch.equal(b[-8192:], tail)
+    del a, b, h, z
+    torch.cuda.empty_cache()
+
+
+def test_hybrid_equals_explicit_methods_full_size(pg, torch):
+    """cfg4 at 1e8 elements: the bucketed hybrid result equals, element for element, what each
+    explicitly requested method produces on the elements the dispatch rule assigns to it
+    (src/pgm_random.c:105-121); every bucket is non-empty; everything is finite."""
+    n = 100_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(20240)
+    h = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 199.9 + 0.1
+    z = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 100 - 50
+    h[::50] = torch.randint(1, 5, (len(h[::50]),), device="cuda", generator=g).double()
+    out = pg.random_polyagamma(h, z, random_state=(12345, 0), disable_checks=True)
+    assert bool(torch.isfinite(out).all()) and bool((out > 0).all())
+    normal = h > 50
+    saddle = ~normal & ((h >= 8) | ((h > 4) & (z <= 4)))
+    dev = ~normal & ~saddle & ((h == 1) | ((h == torch.floor(h)) & (z <= 1)))
+    alt = ~normal & ~saddle & ~dev
+    for name, mask in (("saddle", saddle), ("devroye", dev), ("alternate", alt)):
+        idx = mask.nonzero().squeeze(1)
+        assert idx.numel() > 0
+        idx = idx[:: max(1, idx.numel() // 200_000)]
+        # same global indices -> same streams: run the explicit method on the whole array slice
+        sub = torch.stack([pg.random_polyagamma(h[i:i + 1], z[i:i + 1], method=name, random_state=(12345, 0),
+                                                first_index=int(i), disable_checks=True)[0]
+                           for i in idx[:64].tolist()])
+        assert torch.equal(sub, out[idx[:64]]), name
+    # moments of the normal bucket: standardised residuals ~ N(0, 1)
+    hn, zn, on = h[normal][:5_000_000].cpu().numpy(), z[normal][:5_000_000].cpu().numpy(), out[normal][:5_000_000].cpu().numpy()
+    m = hn * np.tanh(zn / 2) / (2 * zn)
+    a = np.abs(zn)
+    e = np.exp(-a)
+    v = 0.25 * hn * 2 * (1 - e * e - 2 * a * e) / ((1 + e) ** 2 * a**3)
+    big = a >= 1
+    r = (on[big] - m[big]) / np.sqrt(v[big])
+    assert abs(r.mean()) < 4 / np.sqrt(r.size) and abs(r.var() - 1) < 4 * np.sqrt(2 / r.size)
+    del h, z, out
+    torch.cuda.empty_cache()
+
+
+def test_invalid_h_and_edge_sizes(pg, torch):
+    h = _cuda(torch, [1.0, -1.0, 0.0, np.nan, np.inf, -np.inf, 2.0, 60.0, 9.0])
+    z = torch.zeros_like(h)
+    for method in (None, "devroye", "alternate", "saddle", "gamma"):
+        out = pg.random_polyagamma(h, z, method=method, disable_checks=True, random_state=(1, 0)).cpu().numpy()
+        assert np.isfinite(out[[0, 6, 7, 8]]).all(), method
+        assert np.isnan(out[[1, 2, 3, 5]]).all(), method
+        assert np.isposinf(out[4]), method
+    assert pg.random_polyagamma(h[:0], z[:0], disable_checks=True).shape == (0,)
+    assert pg.random_polyagamma(1.0, 0.0, size=0).shape == (0,)
+    one = pg.random_polyagamma(h[:1], z[:1], random_state=(1, 0))
+    assert one.shape == (1,) and float(one[0]) > 0
+    # devroye with h < 1 truncates to zero draws (src/pgm_devroye.c:221)
+    assert float(pg.random_polyagamma(_cuda(torch, [0.5]), _cuda(torch, [1.0]), method="devroye",
+                                      disable_checks=True)[0]) == 0.0
+    # z = NaN behaves as z = 0
+    a = pg.random_polyagamma(_cuda(torch, [1.0]), _cuda(torch, [np.nan]), method="devroye", random_state=(4, 0))
+    b = pg.random_polyagamma(_cuda(torch, [1.0]), _cuda(torch, [0.0]), method="devroye", random_state=(4, 0))
+    assert torch.equal(a, b)
+
+
+def test_strided_broadcast_equals_materialised(pg, torch):
+    rng = np.random.default_rng(2)
+    h = _cuda(torch, rng.uniform(0.5, 60, (4, 5, 1)))
+    z = _cuda(torch, rng.uniform(-8, 8, (7,)))
+    a = pg.random_polyagamma(h, z, random_state=(8, 0))
+    assert a.shape == (4, 5, 7)
+    hb, zb = torch.broadcast_tensors(h, z)
+    b = pg.random_polyagamma(hb.contiguous().reshape(-1), zb.contiguous().reshape(-1), random_state=(8, 0))
+    assert torch.equal(a.reshape(-1), b)
+    c = pg.random_polyagamma(h.transpose(0, 1), 2.0, random_state=(8, 0))  # non-contiguous operand
+    d = pg.random_polyagamma(h.transpose(0, 1).contiguous(), 2.0, random_state=(8, 0))
+    assert torch.equal(c, d)
+
+
+def test_host_buffer_path_equals_device_path(pg, torch):
+    """pgm_cuda_random_polyagamma_fill2_host (pipelined H2D/compute/D2H) vs device pointers."""
+    rng = np.random.default_rng(3)
+    n = (1 << 23) * 2 + 12345  # spans three ring slots
+    h = rng.uniform(0.1, 120, n)
+    z = rng.uniform(-20, 20, n)
+    host = pg.random_polyagamma(h, z, random_state=(6, 2), disable_checks=True)
+    devr = pg.random_polyagamma(_cuda(torch, h), _cuda(torch, z), random_state=(6, 2), disable_checks=True)
+    assert isinstance(host, np.ndarray) and np.array_equal(host, devr.cpu().numpy())
+    host1 = pg.random_polyagamma(1.0, z, random_state=(6, 2), disable_checks=True)  # scalar h broadcast
+    dev1 = pg.random_polyagamma(torch.ones(n, dtype=torch.float64, device="cuda"), _cuda(torch, z),
+                                random_state=(6, 2), disable_checks=True)
+    assert np.array_equal(host1, dev1.cpu().numpy())
+
+
+def test_c_abi_direct_call(torch, oracle):
+    """Straight through ctypes, no Python layer: device pointers in, device pointer out."""
+    from polyagamma_b200 import _lib
+
+    L = _lib.lib()
+    n = 4096
+    h = torch.full((n,), 3.0, dtype=torch.float64, device="cuda")
+    z = torch.linspace(-5, 5, n, dtype=torch.float64, device="cuda")
+    out = torch.empty(n, dtype=torch.float64, device="cuda")
+    before = L.pgm_cuda_launch_count()
+    rc = L.pgm_cuda_random_polyagamma_fill2(11, 4, ctypes.c_void_p(h.data_ptr()), ctypes.c_void_p(z.data_ptr()),
+                                            _lib.HYBRID, n, ctypes.c_void_p(out.data_ptr()), 100, None)
+    torch.cuda.synchronize()
+    assert rc == 0 and L.pgm_cuda_launch_count() > before
+    want = oracle.fill2(11, 4, h.cpu().numpy(), z.cpu().numpy(), first_index=100)
+    assert _frac_agree(out.cpu().numpy(), want) >= 1.0 - MAX_FLIPPED
+    assert L.pgm_cuda_random_polyagamma_fill2(11, 4, None, None, _lib.HYBRID, n, None, 0, None) == _lib.EINVAL
+    assert L.pgm_cuda_random_polyagamma_fill(11, 4, 1.0, 0.0, 17, n, ctypes.c_void_p(out.data_ptr()), 0, None) == _lib.EINVAL
+    v = L.pgm_cuda_random_polyagamma(11, 4, 1.0, 0.0, _lib.HYBRID)
+    assert v == oracle.fill(11, 4, 1.0, 0.0, 1)[0] or abs(v / oracle.fill(11, 4, 1.0, 0.0, 1)[0] - 1) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------
+# densities
+# ------------------------------------------------------------------------------------------
+DENS = (("pdf", "pdf", False), ("cdf", "cdf", False), ("logpdf", "pdf", True), ("logcdf", "cdf", True))
+
+
+def _density_err(got, want, cond, log):
+    """Relative error (absolute near zero for log-densities ~ 0), tolerance scaled by the
+    condition number of the alternating series (SURVEY 8-DEFECTS g)."""
+    fin = np.isfinite(want) & np.isfinite(got) & (np.abs(want) > 1e-290)
+    scale = np.maximum(np.abs(want), 1.0) if log else np.abs(want)
+    with np.errstate(all="ignore"):
+        err = np.abs(got - want) / scale
+    tol = RTOL_DENSITY * np.maximum(1.0, cond / 1e2)
+    return fin, err, tol
+
+
+@pytest.mark.parametrize("name,kind,log", DENS)
+def test_density_golden_grid(pg, density_golden, oracle, name, kind, log):
+    g = density_golden
+    f = pg.polyagamma_pdf if kind == "pdf" else pg.polyagamma_cdf
+    got = f(g["x"], g["h"], g["z"], return_log=log)
+    _, cond = oracle.density(name, g["x"], g["h"], g["z"], return_cond=True)
+    fin, err, tol = _density_err(got, g[name], cond, log)
+    well = fin & (cond < 1e3)
+    assert well.mean() > 0.3
+    assert np.all(err[well] <= tol[well]), float(err[well].max())
+    # exact special values wherever the reference has them
+    assert np.array_equal(np.isneginf(got), np.isneginf(g[name]))
+
+
+@pytest.mark.parametrize("name,kind,log", DENS)
+def test_density_vs_oracle_fresh_grid(pg, oracle, name, kind, log):
+    rng = np.random.default_rng(17)
+    n = 200_000 if name != "logcdf" else 20_000
+    x = rng.uniform(1e-3, 12.5, n)
+    h = rng.uniform(0.5, 25, n)
+    z = rng.uniform(-10, 10, n)
+    z[::13] = 0.0
+    f = pg.polyagamma_pdf if kind == "pdf" else pg.polyagamma_cdf
+    got = f(x, h, z, return_log=log)
+    want, cond = oracle.density(name, x, h, z, return_cond=True)
+    fin, err, tol = _density_err(got, want, cond, log)
+    well = fin & (cond < 1e6)
+    assert np.all(err[well] <= tol[well]), float((err[well] / tol[well]).max())
+
+
+def test_density_edge_values_and_broadcast(pg, torch):
+    # tests/test_polyagamma.py:189-206
+    assert pg.polyagamma_pdf(0) == 0 and pg.polyagamma_pdf(np.inf) == 0 and pg.polyagamma_pdf(-1) == 0
+    assert pg.polyagamma_pdf(0, return_log=True) == -np.inf
+    assert pg.polyagamma_pdf(np.inf, return_log=True) == -np.inf
+    assert pg.polyagamma_cdf(0) == 0 and pg.polyagamma_cdf(np.inf) == 1 and pg.polyagamma_cdf(-1) == 0
+    assert pg.polyagamma_cdf(0, return_log=True) == -np.inf
+    assert pg.polyagamma_cdf(np.inf, return_log=True) == 0
+    assert isinstance(pg.polyagamma_pdf(0.2), float)
+    assert pg.polyagamma_pdf(0.2) == pytest.approx(2.339176537265802, rel=1e-12)
+    assert pg.polyagamma_pdf(3.0, h=6, z=1) == pytest.approx(0.012537773310487178, rel=1e-11)
+    # tests/test_polyagamma.py:213-221
+    assert np.isclose(pg.polyagamma_cdf(0.01, h=10, z=3, return_log=True), -1238.6998500970105)
+    assert np.isclose(pg.polyagamma_cdf(1e-3, h=10, z=3, return_log=True), -12489.8793293567)
+    assert np.isclose(pg.polyagamma_pdf(1e-3, h=10, z=3, return_log=True), -12473.46649418656)
+    assert np.isclose(pg.polyagamma_cdf(1e-16, return_log=True), -1250000000000017.2)
+    assert np.isclose(pg.polyagamma_pdf(1e-16, return_log=True), -1249999999999945.8)
+    x = np.linspace(0.05, 3, 11)[:, None]
+    h = np.array([0.5, 1, 4])[None, :]
+    out = pg.polyagamma_pdf(x, h, 1.5)
+    assert isinstance(out, np.ndarray) and out.shape == (11, 3)
+    flat = pg.polyagamma_pdf(np.broadcast_to(x, (11, 3)).ravel(), np.broadcast_to(h, (11, 3)).ravel(), 1.5)
+    assert np.array_equal(out.ravel(), flat)
+    dev = pg.polyagamma_cdf(torch.from_numpy(x).cuda(), torch.from_numpy(h).cuda(), 1.5)
+    assert dev.is_cuda and dev.shape == (11, 3)
+    assert np.array_equal(dev.cpu().numpy(), pg.polyagamma_cdf(x, h, 1.5))
+    assert pg.polyagamma_pdf(np.empty((0, 3)), h).shape == (0, 3)
+
+
+def test_density_full_size_properties(pg, torch):
+    """cfg5a: 1e4 x 1e4 broadcast grid, all four functions, checked through properties:
+    evenness in z, exp(log f) = f, 0 <= cdf <= 1 and monotone in x, strided == materialised."""
+    rng = np.random.default_rng(20240)
+    m = 10_000
+    x = torch.linspace(1e-3, 12.5, m, dtype=torch.float64, device="cuda")[:, None]
+    h = _cuda(torch, rng.uniform(0.5, 10, m))[None, :]
+    z = _cuda(torch, rng.uniform(-10, 10, m))[None, :]
+    pdf = pg.polyagamma_pdf(x, h, z)
+    assert pdf.shape == (m, m)
+    assert torch.equal(pdf, pg.polyagamma_pdf(x, h, -z))
+    lpdf = pg.polyagamma_pdf(x, h, z, return_log=True)
+    # far in the right tail the alternating sum cancels to <= 0 and log() is NaN, in the
+    # reference too (SURVEY 8-DEFECTS g); everywhere else exp(logpdf) must reproduce pdf
+    # and is rounding noise in both versions; where the density is within 1e-4 of its peak over x
+    # the series is well conditioned and exp(logpdf) must reproduce pdf
+    big = (pdf > 1e-4 * pdf.max(dim=0, keepdim=True).values) & torch.isfinite(lpdf)
+    assert float(big.double().mean()) > 0.2
+    assert float(((lpdf.exp() - pdf).abs() / pdf)[big].max()) < 1e-9
+    del lpdf, big
+    cdf = pg.polyagamma_cdf(x, h, z)
+    assert float(cdf.min()) > -1e-9 and float(cdf.max()) < 1 + 1e-9
+    assert float((cdf[1:] - cdf[:-1]).min()) > -1e-9
+    sub = pg.polyagamma_cdf(x[:64].expand(64, m).contiguous(), h.expand(64, m).contiguous(),
+                            z.expand(64, m).contiguous())
+    assert torch.equal(sub, cdf[:64])
+    # pdf is the x-derivative of cdf: central differences on the fine grid (dx = 1.25e-3)
+    dx = float(x[1] - x[0])
+    num = (cdf[2:] - cdf[:-2]) / (2 * dx)
+    mid = pdf[1:-1]
+    ok = (mid > 1e-3) & (x[1:-1] > 0.05)
+    assert float(((num - mid).abs() / mid)[ok].max()) < 5e-3
+    del pdf, cdf, sub, num, mid, ok
+    lc = pg.polyagamma_cdf(x[::16], h[:, ::16], z[:, ::16], return_log=True)
+    assert bool((lc <= 1e-12).all())
+    torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("name,kind,log", DENS)
+def test_density_vs_compiled_reference(pg, ref, oracle, name, kind, log):
+    """When oracle/_ref travelled to this box: the reference's own compiled C functions."""
+    rng = np.random.default_rng(23)
+    n = 20_000 if name != "logcdf" else 3000
+    x = rng.uniform(1e-3, 10, n)
+    h = rng.uniform(0.5, 20, n)
+    z = rng.uniform(-10, 10, n)
+    f = pg.polyagamma_pdf if kind == "pdf" else pg.polyagamma_cdf
+    got = f(x, h, z, return_log=log)
+    with np.errstate(all="ignore"):
+        want = ref.c_density(name, x, h, z)
+    _, cond = oracle.density(name, x, h, z, return_cond=True)
+    fin, err, tol = _density_err(got, want, cond, log)
+    well = fin & (cond < 1e6)
+    assert np.all(err[well] <= tol[well])
+
+
+# ------------------------------------------------------------------------------------------
+# statistics at 1e7 draws per cell (north_star: mean/var within 4 SE, KS vs cdf, two-sample KS)
+# ------------------------------------------------------------------------------------------
+N_STAT = 10_000_000
+
+STAT_CELLS = [
+    ("devroye", 1, 0), ("devroye", 1, 2.5), ("devroye", 2, -5), ("devroye", 4, 1), ("devroye", 1, 50),
+    ("alternate", 1, 0), ("alternate", 1.5, 0), ("alternate", 2.5, 0), ("alternate", 3.5, 1), ("alternate", 4, 0),
+    ("alternate", 2.7, 30), ("alternate", 6.5, 10), ("alternate", 2, 2),
+    ("saddle", 15, 1), ("saddle", 30, 5), ("saddle", 10, 20), ("saddle", 50, 20),
+    ("saddle", 10, 50), ("saddle", 25, 35), ("saddle", 50, 30), ("saddle", 100, 30),
+    (None, 60, 0), (None, 60, 5), (None, 120, 0), (None, 200, 38), (None, 60, 40), (None, 100, 50),
+    (None, 1, 0), (None, 3, 0.5), (None, 3, 2.5), (None, 2.5, 0),
+]
+
+
+@pytest.mark.parametrize("method,h,z", STAT_CELLS)
+def test_exact_moments_1e7(pg, torch, method, h, z):
+    x = pg.random_polyagamma(float(h), float(z), size=N_STAT, method=method, random_state=(2024, 0), device="cuda")
+    mean, var = pg_moments(h, z)
+    n = x.numel()
+    xm = float(x.mean())
+    xc = x - xm
+    v = float((xc * xc).mean())
+    m4 = float((xc**4).mean())
+    zm = (xm - mean) / np.sqrt(var / n)
+    zv = (v - var) / np.sqrt((m4 - var * var) / n)
+    assert abs(zm) < 4 and abs(zv) < 4, (zm, zv)
+
+
+@pytest.mark.parametrize("h,z", [(1, 0), (0.5, 2), (2.5, 50), (0.1, 1)])
+def test_gamma_truncated_moments(pg, h, z):
+    x = pg.random_polyagamma(float(h), float(z), size=2_000_000, method="gamma", random_state=(2024, 1))
+    zm, zv = moment_zscores(x, *gamma_sum_moments(h, z))
+    assert abs(zm) < 4 and abs(zv) < 4, (zm, zv)
+
+
+@pytest.mark.parametrize("method,h,z", [("devroye", 1, 0), ("devroye", 2, -5), ("alternate", 1.5, 0),
+                                        ("alternate", 2.5, 0), ("alternate", 3.5, 1), ("alternate", 4, 3),
+                                        (None, 3, 2.5), (None, 1, 1)])
+def test_ks_against_cdf_1e7(pg, torch, method, h, z):
+    """KS of 1e7 draws against polyagamma_cdf (the CUDA cdf, itself parity-checked above against
+    the reference's) for the exact samplers, in cells where the cdf series is well conditioned."""
+    x = pg.random_polyagamma(float(h), float(z), size=N_STAT, method=method, random_state=(2024, 2), device="cuda")
+    xs, _ = torch.sort(x)
+    F = pg.polyagamma_cdf(xs, float(h), float(z))
+    n = xs.numel()
+    i = torch.arange(1, n + 1, device="cuda", dtype=torch.float64)
+    d = max(float((i / n - F).max()), float((F - (i - 1) / n).max()))
+    assert d * np.sqrt(n) < 1.95, d * np.sqrt(n)  # p ~ 1e-3
+
+
+def test_two_sample_vs_golden_reference_quantiles(pg, sampler_golden):
+    from test_oracle_sampler import _mode_for_cell
+
+    g = sampler_golden
+    bad = {}
+    for (mid, h, z), name, q, nref in zip(g["cells"], g["methods"], g["quantiles"], g["nref"]):
+        name = str(name)
+        n = 4_000_000 if name != "gamma" else 200_000
+        x = pg.random_polyagamma(float(h), float(z), size=n, method=None if name == "hybrid" else name,
+                                 random_state=(4242, 1), ref_compat=_mode_for_cell(name, h, z))
+        d = ks_vs_quantiles(x, q, g["probs"], int(nref))
+        if d > 1.95:
+            bad[(name, h, z)] = d
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("method,h,z,compat", [("devroye", 1, 0, False), ("devroye", 3, 2, False),
+                                               ("alternate", 2.5, 0, True), ("alternate", 3.5, 1, True),
+                                               ("alternate", 0.5, 0, False), ("alternate", 2.7, 30, False),
+                                               ("saddle", 4.5, 0, True), ("saddle", 10, 2, False),
+                                               ("saddle", 30, 5, False), (None, 60, 5, False),
+                                               (None, 2.5, 3, True)])
+def test_two_sample_ks_vs_live_reference_1e7(pg, ref, method, h, z, compat):
+    """Two-sample KS at 1e7 draws against the compiled reference drawing with numpy PCG64, in
+    the mode the defect register says must agree (default where the reference is clean,
+    ref_compat where its envelope constants bias it)."""
+    from scipy import stats
+
+    x = pg.random_polyagamma(float(h), float(z), size=N_STAT, method=method, random_state=(31337, 0),
+                             ref_compat=compat)
+    y = ref.random_polyagamma(h, z, size=N_STAT, method=method,
+                              random_state=np.random.Generator(np.random.PCG64(99)))
+    r = stats.ks_2samp(x, y)
+    assert r.statistic * np.sqrt(N_STAT / 2) < 1.95, r
