@@ -114,7 +114,8 @@ def launch_count() -> int:
     return int(lib().pgm_cuda_launch_count())
 
 
-KERNEL_KINDS = ("classify", "scan", "scatter", "devroye", "alternate", "saddle", "normal", "gamma", "density")
+KERNEL_KINDS = ("classify", "scan", "scatter", "devroye", "alternate", "saddle", "normal", "gamma", "density",
+                "setup", "saddle_left")
 
 
 def profile_begin() -> None:

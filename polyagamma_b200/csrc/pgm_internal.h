@@ -63,7 +63,9 @@ enum : int {
     kKindNormal = 6,
     kKindGamma = 7,
     kKindDensity = 8,
-    kNumKinds = 9
+    kKindSetup = 9,
+    kKindSaddleLeft = 10,
+    kNumKinds = 11
 };
 
 class ScopedKernelTimer {

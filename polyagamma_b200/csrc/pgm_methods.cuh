@@ -1,16 +1,22 @@
-// pgm_methods.cuh -- the per-element sampling methods as lane-level state machines.
+// pgm_methods.cuh -- the per-element sampling methods, split the way the GPU wants them.
 //
-// Each method M provides
-//     struct Par    per-(h, z) constants          (the reference's parameter_t)
-//     struct State  per-element progress          (partial sum, pieces left)
-//     setup(par, h, z, compat)                    (the reference's set_sampling_parameters)
-//     begin(par, st, h, z, compat)
-//     step(par, st, rng, compat) -> bool          ONE proposal attempt; true when the element is
-//                                                 complete and st.acc holds PG(h, z)
-// so that a persistent warp can interleave 32 elements at proposal granularity: a lane that
-// rejects simply takes another step, a lane that finishes is retired and refilled.  Every lane
-// consumes its element's Philox stream in exactly the order of the scalar oracle
-// (oracle/pgm_oracle.c), which is what makes results independent of launch shape.
+// The reference does "set_sampling_parameters(h, z); loop { propose; accept? }" per element
+// (fill2 pays the setup for every element).  Here each method M is cut into
+//
+//   make_record(h, z, compat, rec[])   dense, divergence-free part: everything that depends
+//                                      only on (h, z) and is expensive (erfc, lgamma, incomplete
+//                                      gamma, Newton solves ...).  Run by setup_kernel<M> over a
+//                                      whole bucket, one thread per element, result written as
+//                                      M::kFields doubles per element (structure of arrays).
+//   load(rec, par, st)                 cheap: rebuild the lane's working set from the record
+//   step(par, st, rng) -> bool         ONE proposal attempt; true when the element is complete
+//                                      and st.acc holds PG(h, z)
+//
+// so the persistent sampling kernel only carries the small `step` code (instruction-cache
+// resident) and a warp interleaves 32 elements at proposal granularity: a lane that rejects
+// just takes another step, a lane that finishes is retired and refilled.  Every lane consumes
+// its element's Philox stream in exactly the order of the scalar oracle (oracle/pgm_oracle.c),
+// which is what makes results independent of launch shape.
 //
 // Restates: src/pgm_devroye.c, src/pgm_alternate.c (+ _trunc_points.h), src/pgm_saddle.c and
 // the normal / gamma-convolution samplers of src/pgm_random.c, all in FP64.
@@ -20,14 +26,17 @@
 
 namespace pgm {
 
+constexpr int kMaxRecordFields = 10;
+
 // =========================================================================================
 // Devroye: exact J*(1, z), summed floor(h) times            (src/pgm_devroye.c)
 // =========================================================================================
 struct Devroye {
     static constexpr double T = 0.64;
+    static constexpr int kFields = 4;  // w, K, zz, count
 
     struct Par {
-        double w;  // p / (p + q): probability of the truncated inverse-Gaussian piece
+        double w;   // p / (p + q): probability of the truncated inverse-Gaussian piece
         double K;
         double zz;  // |z| / 2
         double z2;
@@ -38,37 +47,45 @@ struct Devroye {
     };
 
     // set_sampling_parameters (src/pgm_devroye.c:61-83)
-    static __device__ __forceinline__ void setup(Par& p, double /*h*/, double z, bool /*compat*/)
+    static __device__ __forceinline__ void make_record(double h, double z, bool /*compat*/, double* rec)
     {
-        p.zz = 0.5 * fabs(z);
-        if (!(p.zz > 0.0)) p.zz = 0.0;  // z = NaN is sampled as z = 0
-        if (p.zz > 0.0) {
+        double zz = 0.5 * fabs(z);
+        if (!(zz > 0.0)) zz = 0.0;  // z = NaN is sampled as z = 0
+        double w, K;
+        if (zz > 0.0) {
             const double a = 0.8838834764831844;  // 1 / sqrt(2T)
             const double tt = 0.565685424949238;  // sqrt(T / 2)
-            double b = p.zz * tt;
-            double t1 = erfc(a - b) * exp(-p.zz);
-            double t2 = (a + b < 26.5) ? erfc(a + b) * exp(p.zz) : 0.0;
+            double b = zz * tt;
+            double t1 = erfc(a - b) * exp(-zz);
+            double t2 = (a + b < 26.5) ? erfc(a + b) * exp(zz) : 0.0;
             double pp = t1 + t2;
-            p.z2 = p.zz * p.zz;
-            p.K = kPi2_8 + 0.5 * p.z2;
-            double q = kPi_2 * exp(-p.K * T) / p.K;
-            p.w = (pp + q > 0.0) ? pp / (pp + q) : 1.0;
+            K = kPi2_8 + 0.5 * zz * zz;
+            double q = kPi_2 * exp(-K * T) / K;
+            w = (pp + q > 0.0) ? pp / (pp + q) : 1.0;
         }
         else {
-            p.w = 0.4223027567786595;  // src/pgm_devroye.c:78
-            p.K = kPi2_8;
-            p.z2 = 0.0;
+            w = 0.4223027567786595;  // src/pgm_devroye.c:78
+            K = kPi2_8;
         }
-    }
-
-    static __device__ __forceinline__ void begin(Par&, State& s, double h, double, bool)
-    {
-        s.acc = 0.0;
+        rec[0] = w;
+        rec[1] = K;
+        rec[2] = zz;
         // `size_t hi = h` (src/pgm_devroye.c:221); counts above 2^32-1 are clamped
-        s.remaining = (h >= 4294967295.0) ? 4294967295u : (uint32_t)h;
+        rec[3] = (h >= 4294967295.0) ? 4294967295.0 : floor(h);
     }
 
-    static __device__ __forceinline__ bool empty(const State& s) { return s.remaining == 0; }
+    // false: nothing to draw (floor(h) == 0), the sample is 0
+    template <class Rec>
+    static __device__ __forceinline__ bool load(const Rec& rec, Par& p, State& s, bool)
+    {
+        p.w = rec[0];
+        p.K = rec[1];
+        p.zz = rec[2];
+        p.z2 = p.zz * p.zz;
+        s.acc = 0.0;
+        s.remaining = (uint32_t)rec[3];
+        return s.remaining != 0;
+    }
 
     // random_right_bounded_invgauss (src/pgm_devroye.c:113-142)
     static __device__ __forceinline__ double trunc_invgauss(const Par& p, Rng& r)
@@ -108,7 +125,7 @@ struct Devroye {
     }
 
     // One pass of the loop in random_jacobi_star (src/pgm_devroye.c:160-190)
-    static __device__ __forceinline__ bool step(const Par& p, State& s, Rng& r, bool)
+    static __device__ __forceinline__ bool step(Par& p, State& s, Rng& r, bool)
     {
         double x, lp, e;
         if (r.uniform_co() < p.w) {
@@ -165,14 +182,18 @@ static __constant__ double c_trunc_f[25] = {
     7.473186206, 7.734284136, 7.995175158, 8.255882407};
 
 struct Alternate {
+    // h, zz, then (w_right, lgamma(h)) of the first piece and of the remainder piece
+    static constexpr int kFields = 6;
+
     struct Par {
         double w_right;  // q / (p + q): probability of the truncated-gamma (right) piece
         double h, zz, z2, t, t_inv, lambda, half_h2, lgammah, hlog2, h_z, h_z2, ca;
     };
     struct State {
         double acc;
-        double h_rem;   // shape still to be drawn after the current piece
-        double chunk;   // 0 when the current piece is the last one
+        double h_rem;  // shape still to be drawn, including the current piece (chunked only)
+        double chunk;  // 0 when the current piece is the last one
+        double w_last, lg_last;  // record of the remainder piece
     };
 
     // get_truncation_point (src/pgm_alternate.c:38-70) as a true linear interpolation
@@ -186,63 +207,99 @@ struct Alternate {
         return c_trunc_f[i] + (c_trunc_f[i + 1] - c_trunc_f[i]) * frac;
     }
 
-    // set_sampling_parameters (src/pgm_alternate.c:139-176); mixture weight in log space
-    static __device__ inline void setup_piece(Par& p, double h, double zz, bool compat)
+    // the expensive half of set_sampling_parameters (src/pgm_alternate.c:139-176): the mixture
+    // weight q / (p + q), in log space, and lgamma(h)
+    static __device__ inline void piece_weights(double h, double zz, double& w_right, double& lgammah)
     {
+        double t = trunc_point(h);
+        lgammah = pgm_lgamma(h);
+        double hlog2 = h * kLog2;
+        double lp, lambda;
+        double a = h / sqrt(2.0 * t);
+        if (zz > 0.0) {
+            lambda = kPi2_8 + 0.5 * zz * zz;
+            double b = zz * sqrt(0.5 * t);
+            double hz = h * zz;
+            double t1 = 0.5 * erfc(a - b) * exp(-hz);
+            double t2 = (a + b < 26.5 && hz < 700.0) ? 0.5 * erfc(a + b) * exp(hz) : 0.0;
+            lp = hlog2 + log(t1 + t2);
+        }
+        else {
+            lambda = kPi2_8;
+            lp = hlog2 + log(erfc(a));
+        }
+        double lq = h * (kLogPi_2 - log(lambda)) + log_upper_gamma(h, lambda * t, true);
+        w_right = 1.0 / (1.0 + exp(lp - lq));
+        if (!(w_right >= 0.0)) w_right = 0.0;
+    }
+
+    // piece schedule of random_polyagamma_alternate (src/pgm_alternate.c:294-323)
+    static __device__ inline void make_record(double h, double z, bool /*compat*/, double* rec)
+    {
+        double zz = 0.5 * fabs(z);
+        if (!(zz > 0.0)) zz = 0.0;
+        rec[0] = h;
+        rec[1] = zz;
+        if (h > 4.0) {
+            double chunk = (h >= 5.0) ? 4.0 : 3.0;
+            double hr = h;
+            while (hr > 4.0) hr -= chunk;
+            piece_weights(chunk, zz, rec[2], rec[3]);
+            piece_weights(hr, zz, rec[4], rec[5]);
+        }
+        else {
+            piece_weights(h, zz, rec[2], rec[3]);
+            rec[4] = 0.0;
+            rec[5] = 0.0;
+        }
+    }
+
+    // the cheap half of set_sampling_parameters
+    static __device__ __forceinline__ void set_piece(Par& p, double h, double zz, double w_right, double lgammah,
+                                                     bool compat)
+    {
+        p.w_right = w_right;
+        p.lgammah = lgammah;
         p.h = h;
         p.zz = zz;
         p.t = trunc_point(h);
         p.t_inv = 1.0 / p.t;
         p.half_h2 = 0.5 * h * h;
-        p.lgammah = pgm_lgamma(h);
         p.hlog2 = h * kLog2;
         p.ca = compat ? 0.5 * kLogPi_2 : kLogPi_2;  // src/pgm_alternate.c:90
-        double lp;
-        double a = h / sqrt(2.0 * p.t);
+        p.z2 = zz * zz;
+        p.lambda = kPi2_8 + 0.5 * p.z2;
         if (zz > 0.0) {
-            p.z2 = zz * zz;
             p.h_z = h / zz;
             p.h_z2 = p.h_z * p.h_z;
-            p.lambda = kPi2_8 + 0.5 * p.z2;
-            double b = zz * sqrt(0.5 * p.t);
-            double hz = h * zz;
-            double t1 = 0.5 * erfc(a - b) * exp(-hz);
-            double t2 = (a + b < 26.5 && hz < 700.0) ? 0.5 * erfc(a + b) * exp(hz) : 0.0;
-            lp = p.hlog2 + log(t1 + t2);
         }
         else {
-            p.z2 = 0.0;
             p.h_z = INFINITY;
             p.h_z2 = INFINITY;
-            p.lambda = kPi2_8;
-            lp = p.hlog2 + log(erfc(a));
         }
-        double lq = h * (kLogPi_2 - log(p.lambda)) + log_upper_gamma(h, p.lambda * p.t, true);
-        p.w_right = 1.0 / (1.0 + exp(lp - lq));
-        if (!(p.w_right >= 0.0)) p.w_right = 0.0;
     }
 
-    static __device__ __forceinline__ void setup(Par&, double, double, bool) {}
-
-    // random_polyagamma_alternate (src/pgm_alternate.c:294-323): piece schedule
-    static __device__ inline void begin(Par& p, State& s, double h, double z, bool compat)
+    template <class Rec>
+    static __device__ __forceinline__ bool load(const Rec& rec, Par& p, State& s, bool compat)
     {
-        double zz = 0.5 * fabs(z);
-        if (!(zz > 0.0)) zz = 0.0;
+        double h = rec[0], zz = rec[1];
         s.acc = 0.0;
         if (h > 4.0) {
             s.chunk = (h >= 5.0) ? 4.0 : 3.0;
             s.h_rem = h;
-            setup_piece(p, s.chunk, zz, compat);
+            s.w_last = rec[4];
+            s.lg_last = rec[5];
+            set_piece(p, s.chunk, zz, rec[2], rec[3], compat);
         }
         else {
             s.chunk = 0.0;
             s.h_rem = 0.0;
-            setup_piece(p, h, zz, compat);
+            s.w_last = 0.0;
+            s.lg_last = 0.0;
+            set_piece(p, h, zz, rec[2], rec[3], compat);
         }
+        return true;
     }
-
-    static __device__ __forceinline__ bool empty(const State&) { return false; }
 
     static __device__ __forceinline__ double inv_left_gamma(const Par& p, Rng& r)
     {
@@ -324,7 +381,7 @@ struct Alternate {
                 double hr = s.h_rem;
                 s.chunk = 0.0;
                 s.h_rem = 0.0;
-                setup_piece(p, hr, p.zz, compat);
+                set_piece(p, hr, p.zz, s.w_last, s.lg_last, compat);
             }
             return false;
         }
@@ -336,154 +393,227 @@ struct Alternate {
 // =========================================================================================
 // Saddle-point approximation                                 (src/pgm_saddle.c)
 // =========================================================================================
-struct Saddle {
+//
+// FULL = false is the specialisation for elements whose right-hand (truncated gamma) envelope
+// piece carries less than 2^-33 of the proposal mass: the 32-bit mixture uniform can then never
+// select it, so neither the right tangent nor the incomplete gamma function is needed and the
+// per-proposal code has a single branch-free path.  saddle_left_only() is the (h, z) rule.
+namespace saddle {
+
+constexpr double kUMax = 1.2337005501361697;  // just below pi^2 / 8, the pole of tan
+
+// K'(u), K''(u), K'''(u) of the cumulant generating function (cumulant_prime,
+// src/pgm_saddle.c:100-107, with exact tan / tanh instead of the rational tanh_x :56-74)
+__device__ __forceinline__ void
+kprime3(double u, double& f, double& fp, double& fpp)
+{
+    double s2 = 2.0 * u;
+    if (fabs(s2) < 1e-4) {
+        double g = 1.0 / 3.0 + s2 * (2.0 / 15.0 + s2 * (17.0 / 315.0));
+        f = 1.0 + s2 * g;
+        fp = f * f - g;
+        fpp = 16.0 / 15.0 + s2 * (136.0 / 105.0);
+        return;
+    }
+    double a = fabs(s2);
+    double rs = rsqrt(a);
+    double s = a * rs;
+    double inv = (s2 > 0.0) ? rs * rs : -(rs * rs);
+    f = ((s2 > 0.0) ? tan(s) : tanh(s)) * rs;
+    double t = (1.0 - f) * inv;
+    fp = f * f + t;
+    fpp = 2.0 * f * fp - fp * inv - 2.0 * t * inv;
+}
+
+// cumulant (src/pgm_saddle.c:91-94) minus its log cosh z offset, from K'(u) = f:
+//   u > 0: -log cos(s)  = 1/2 log(1 + tan^2 s)
+//   u < 0: -log cosh(s) = 1/2 log(1 - tanh^2 s), or -(s - log 2 + log1p(e^-2s)) once tanh -> 1
+__device__ __forceinline__ double
+cumulant0(double u, double f)
+{
+    double s2 = 2.0 * u;
+    if (s2 > 0.0) {
+        return 0.5 * log(1.0 + f * f * s2);
+    }
+    if (s2 < 0.0) {
+        double s = sqrt(-s2);
+        double th = f * s;
+        if (s < 3.0) {
+            return 0.5 * log((1.0 - th) * (1.0 + th));
+        }
+        double e = (1.0 - th) / (1.0 + th);  // e^{-2s}
+        return -(s - kLog2 + e * (1.0 - e * (0.5 - e * (1.0 / 3.0 - 0.25 * e))));
+    }
+    return 0.0;
+}
+
+// select_starting_guess (src/pgm_saddle.c:119-125); for x <= 0.25 the large-argument solution of
+// tanh(s)/s = x replaces the constant -9
+__device__ __forceinline__ double
+table_guess(double x)
+{
+    if (x <= 0.25) {
+        double s = (1.0 - 2.0 * exp(-2.0 / x)) / x;
+        return -0.5 * s * s;
+    }
+    return x <= 0.5 ? -1.78 : x <= 1.0 ? -0.147 : x <= 1.5 ? 0.345 : x <= 2.5 ? 0.72 : x <= 4.0 ? 0.95 : 1.15;
+}
+
+// newton_raphson (src/pgm_saddle.c:140-158): root u of K'(u) = x, relative residual <= 1e-9.
+// Halley's iteration (uses K''', which is free once K' and K'' are known) falls back to a
+// Newton step when its denominator is not positive.  On return f = K'(u), fp = K''(u) were
+// evaluated AT the returned u.
+__device__ __forceinline__ double
+solve(double x, double u, double& f, double& fp)
+{
+    double fpp;
+    for (int n = 0; n < 30; ++n) {
+        kprime3(u, f, fp, fpp);
+        double g = f - x;
+        if (fabs(g) <= 1e-9 * x || !(fp > 1e-300)) return u;
+        double den = 2.0 * fp * fp - g * fpp;
+        double du = (den > 0.0) ? 2.0 * g * fp / den : g / fp;
+        double un = u - du;
+        if (un >= kUMax) un = 0.5 * (u + kUMax);  // never step onto / over the pole
+        if (un == u) return u;
+        u = un;
+    }
+    kprime3(u, f, fp, fpp);
+    return u;
+}
+
+// invgauss_logcdf (src/pgm_saddle.c:282-292)
+__device__ __forceinline__ double
+invgauss_logcdf(double x, double mu, double lambda)
+{
+    double qm = x / mu;
+    double tm = mu / lambda;
+    double rr = sqrt(x / lambda);
+    double a = log_ndtr((qm - 1.0) / rr);
+    double b = 2.0 / tm + log_ndtr(-(qm + 1.0) / rr);
+    return a + log1p(exp(b - a));
+}
+
+}  // namespace saddle
+
+// Elements of the saddle method whose right envelope piece is unreachable (weight < 2^-33, see
+// tools/saddle_right_weight.py for the map of log10 w_right over (h, |z|/2)).  Only used with
+// the consistent envelope; ref_compat keeps the reference's (much larger) right weight.
+__host__ __device__ __forceinline__ bool
+saddle_left_only(double h, double z, bool compat)
+{
+    return !compat && h * (1.0 + 0.125 * fabs(z)) >= 22.0;
+}
+
+template <bool FULL>
+struct SaddleT {
+    // h, zz, xl, c_l, a1, a2 [, w_left, c_r, slope_r]
+    static constexpr int kFields = FULL ? 9 : 6;
+
     struct Par {
-        double w_left;  // p / (p + q): probability of the truncated inverse-Gaussian piece
-        double h, half_z2, log_cosh_z, xl, xc, logxc;
-        double slope_l, icpt_l, slope_r, icpt_r, log_coef_l, log_coef_r, log_sqrt_h2pi, hrho;
+        double h, half_z2, xl, xc, slope_l, c_l, a1, a2;
+        double w_left, c_r, slope_r;  // FULL only
     };
     struct State {
         double acc;
     };
 
-    static __device__ __forceinline__ double log_cosh(double s)
+    // set_sampling_parameters (src/pgm_saddle.c:180-230) + mixture weight (:317-328, log space)
+    static __device__ inline void make_record(double h, double z, bool compat, double* rec)
     {
-        s = fabs(s);
-        return s + log1p(exp(-2.0 * s)) - kLog2;
-    }
-
-    // cumulant_prime (src/pgm_saddle.c:100-107) with exact tan / tanh
-    static __device__ __forceinline__ void kprime(double u, double& f, double& fp)
-    {
-        double s2 = 2.0 * u;
-        if (fabs(s2) < 1e-4) {
-            double g = 1.0 / 3.0 + s2 * (2.0 / 15.0 + s2 * (17.0 / 315.0));
-            f = 1.0 + s2 * g;
-            fp = f * f - g;
-            return;
-        }
-        if (s2 > 0.0) {
-            double s = sqrt(s2);
-            f = tan(s) / s;
-        }
-        else {
-            double s = sqrt(-s2);
-            f = tanh(s) / s;
-        }
-        fp = f * f + (1.0 - f) / s2;
-    }
-
-    // cumulant (src/pgm_saddle.c:91-94) minus its log cosh z offset
-    static __device__ __forceinline__ double cumulant0(double u)
-    {
-        if (u < 0.0) return -log_cosh(sqrt(-2.0 * u));
-        if (u > 0.0) return -log(cos(sqrt(2.0 * u)));
-        return 0.0;
-    }
-
-    // select_starting_guess (src/pgm_saddle.c:119-125)
-    static __device__ __forceinline__ double guess(double x)
-    {
-        if (x <= 0.25) {
-            double s = (1.0 - 2.0 * exp(-2.0 / x)) / x;
-            return -0.5 * s * s;
-        }
-        return x <= 0.5 ? -1.78 : x <= 1.0 ? -0.147 : x <= 1.5 ? 0.345 : x <= 2.5 ? 0.72
-               : x <= 4.0 ? 0.95 : 1.15;
-    }
-
-    // newton_raphson (src/pgm_saddle.c:140-158)
-    static __device__ inline double newton(double x, double& fprime)
-    {
-        const double umax = 1.2337005501361697;
-        double u = guess(x);
-        double f, fp;
-        for (int n = 0; n < 25; ++n) {
-            kprime(u, f, fp);
-            double fval = f - x;
-            if (fabs(fval) <= 1e-9 * x || !(fp > 1e-300)) break;
-            double un = u - fval / fp;
-            if (un >= umax) un = 0.5 * (u + umax);
-            if (un == u) break;
-            u = un;
-        }
-        kprime(u, f, fp);
-        fprime = fp;
-        return u;
-    }
-
-    // invgauss_logcdf (src/pgm_saddle.c:282-292)
-    static __device__ __forceinline__ double invgauss_logcdf(double x, double mu, double lambda)
-    {
-        double qm = x / mu;
-        double tm = mu / lambda;
-        double rr = sqrt(x / lambda);
-        double a = log_ndtr((qm - 1.0) / rr);
-        double b = 2.0 / tm + log_ndtr(-(qm + 1.0) / rr);
-        return a + log1p(exp(b - a));
-    }
-
-    // set_sampling_parameters (src/pgm_saddle.c:180-230) + mixture weight (:317-328)
-    static __device__ inline void setup(Par& p, double h, double z, bool compat)
-    {
+        using namespace saddle;
         double zz = 0.5 * fabs(z);
         if (!(zz > 0.0)) zz = 0.0;
-        double xl, logxl;
+        double xl, logxl, half_z2, log_cosh_z;
         if (zz > 0.0) {
-            xl = tanh(zz) / zz;
+            double e = exp(-2.0 * zz);
+            xl = (1.0 - e) / ((1.0 + e) * zz);  // tanh(zz) / zz
             logxl = log(xl);
-            p.half_z2 = 0.5 * zz * zz;
-            p.log_cosh_z = log_cosh(zz);
+            half_z2 = 0.5 * zz * zz;
+            log_cosh_z = zz + log1p(e) - kLog2;
         }
         else {
             xl = 1.0;
             logxl = 0.0;
-            p.half_z2 = 0.0;
-            p.log_cosh_z = 0.0;
+            half_z2 = 0.0;
+            log_cosh_z = 0.0;
         }
-        p.h = h;
-        p.xl = xl;
-        p.xc = 2.75 * xl;
-        double xr = 3.0 * xl;
-        double xc_inv = 1.0 / p.xc;
-        double xl_inv = 1.0 / xl;
-        double fp_r, fp_c;
-        double ur = newton(xr, fp_r);
-        (void)newton(p.xc, fp_c);
-        double tr = ur + p.half_z2;
-
-        p.slope_l = -0.5 * xl_inv * xl_inv;
-        p.icpt_l = -0.5 * xc_inv + xl_inv;
-        p.logxc = 1.0116009116784799 + logxl;
-        p.slope_r = -tr - 1.0 / xr;
-        p.icpt_r = (p.log_cosh_z + cumulant0(ur)) + 1.0 - 1.0986122886681098 - logxl + p.logxc;
-
-        double alpha_r = fp_c * xc_inv * xc_inv;
-        double alpha_l = xc_inv * alpha_r;
-        p.log_sqrt_h2pi = 0.5 * log(h / (2.0 * kPi));
-        p.log_coef_l = p.log_sqrt_h2pi - 0.5 * log(alpha_l);
-        p.log_coef_r = p.log_sqrt_h2pi - 0.5 * log(alpha_r);
-
-        double lp = h * (0.5 * xc_inv + p.icpt_l - xl_inv) + invgauss_logcdf(p.xc, xl, h) -
-                    0.5 * log(alpha_l);
-        p.hrho = -h * p.slope_r;
-        double lq = log_upper_gamma(h, p.hrho * p.xc, false) + p.log_coef_r +
-                    h * (p.icpt_r - (compat ? 0.0 : p.logxc) - log(p.hrho));
-        p.w_left = 1.0 / (1.0 + exp(lq - lp));
-        if (!(p.w_left >= 0.0)) p.w_left = 1.0;
+        const double xc = 2.75 * xl;
+        const double xc_inv = 1.0 / xc;
+        const double xl_inv = 1.0 / xl;
+        double f, fp_c;
+        (void)solve(xc, table_guess(xc), f, fp_c);
+        const double alpha_r = fp_c * xc_inv * xc_inv;  // K''(u(xc)) / xc^2
+        const double alpha_l = xc_inv * alpha_r;
+        const double icpt_l = -0.5 * xc_inv + xl_inv;  // cumulant(ul) = 0, src/pgm_saddle.c:216
+        // second-order expansion of u(x) about x = xl, where u = -zz^2/2 exactly:
+        // du/dx = 1 / K'', d2u/dx2 = -K''' / K''^3
+        double f_l, fp_l, fpp_l;
+        kprime3(-half_z2, f_l, fp_l, fpp_l);
+        rec[0] = h;
+        rec[1] = zz;
+        rec[2] = xl;
+        // constant part of  log k_l(x) - log phi(x)  (bounding_kernel :250-263, saddle_point :235-244)
+        rec[3] = 0.5 * h * xc_inv + h * icpt_l - 0.5 * log(alpha_l) - h * log_cosh_z;
+        rec[4] = 1.0 / fp_l;
+        rec[5] = -0.5 * fpp_l / (fp_l * fp_l * fp_l);
+        if (FULL) {
+            const double xr = 3.0 * xl;
+            double fp_r;
+            double ur = solve(xr, table_guess(xr), f, fp_r);
+            const double tr = ur + half_z2;
+            const double logxc = 1.0116009116784799 + logxl;  // log(2.75)
+            const double slope_r = -tr - 1.0 / xr;
+            const double icpt_r = (log_cosh_z + cumulant0(ur, f)) + 1.0 - 1.0986122886681098 - logxl + logxc;
+            const double log_sqrt_h2pi = 0.5 * log(h / (2.0 * kPi));
+            const double log_coef_r = log_sqrt_h2pi - 0.5 * log(alpha_r);
+            double lp = h * (0.5 * xc_inv + icpt_l - xl_inv) + invgauss_logcdf(xc, xl, h) - 0.5 * log(alpha_l);
+            const double hrho = -h * slope_r;
+            double lq = log_upper_gamma(h, hrho * xc, false) + log_coef_r +
+                        h * (icpt_r - (compat ? 0.0 : logxc) - log(hrho));
+            double w_left = 1.0 / (1.0 + exp(lq - lp));
+            if (!(w_left >= 0.0)) w_left = 1.0;
+            rec[6] = w_left;
+            // src/pgm_saddle.c:257 uses +log(xc); the derivation needs -log(xc) (SURVEY 8-DEFECTS i)
+            rec[7] = h * ((compat ? logxc : -logxc) + icpt_r) - 0.5 * log(alpha_r) - h * log_cosh_z;
+            rec[8] = slope_r;
+        }
     }
 
-    static __device__ __forceinline__ void begin(Par&, State& s, double, double, bool) { s.acc = 0.0; }
-    static __device__ __forceinline__ bool empty(const State&) { return false; }
-
-    // One pass of the proposal loop of random_polyagamma_saddle (src/pgm_saddle.c:331-347)
-    static __device__ inline bool step(const Par& p, State& s, Rng& r, bool compat)
+    template <class Rec>
+    static __device__ __forceinline__ bool load(const Rec& rec, Par& p, State& s, bool)
     {
+        p.h = rec[0];
+        double zz = rec[1];
+        p.half_z2 = 0.5 * zz * zz;
+        p.xl = rec[2];
+        p.xc = 2.75 * p.xl;
+        p.slope_l = -0.5 / (p.xl * p.xl);
+        p.c_l = rec[3];
+        p.a1 = rec[4];
+        p.a2 = rec[5];
+        if (FULL) {
+            p.w_left = rec[6];
+            p.c_r = rec[7];
+            p.slope_r = rec[8];
+        }
+        s.acc = 0.0;
+        return true;
+    }
+
+    // One pass of the proposal loop of random_polyagamma_saddle (src/pgm_saddle.c:331-347).
+    // Accept iff  log U + log k(x) <= log phi(x); the common sqrt(h / 2 pi) has been cancelled.
+    static __device__ __forceinline__ bool step(Par& p, State& s, Rng& r, bool)
+    {
+        using namespace saddle;
         const double h = p.h;
         double x;
-        if (r.uniform32() < p.w_left) {
-            double mu = p.xl, mu2 = p.xl * p.xl;
-            do {
+        bool left = true;
+        double um = r.uniform32();  // mixture draw (always consumed, as in the oracle)
+        if (FULL) left = um < p.w_left;
+        if (left) {
+            const double mu = p.xl, mu2 = p.xl * p.xl;
+            do {  // IG(mu = xl, lambda = h) | x < xc, Michael-Schucany-Haas
                 double y = r.normal();
                 double w = mu + 0.5 * mu2 * y * y / h;
                 x = mu2 / (w + sqrt(fmax(w * w - mu2, 0.0)));
@@ -493,22 +623,33 @@ struct Saddle {
             } while (x >= p.xc);
         }
         else {
-            x = left_bounded_gamma(r, h, p.hrho, p.xc);
+            x = left_bounded_gamma(r, h, -h * p.slope_r, p.xc);
         }
-        double logx = log(x);
+        const double logx = log(x);
         double lk;
-        if (x > p.xc) {  // bounding_kernel (src/pgm_saddle.c:250-263)
-            double sgn = compat ? 1.0 : -1.0;
-            lk = h * (sgn * p.logxc + p.slope_r * x + p.icpt_r) + (h - 1.0) * logx + p.log_coef_r;
+        if (FULL && x > p.xc) {
+            lk = h * p.slope_r * x + (h - 1.0) * logx + p.c_r;
         }
         else {
-            lk = 0.5 * h * (1.0 / p.xc - 1.0 / x) + h * (p.slope_l * x + p.icpt_l) - 1.5 * logx +
-                 p.log_coef_l;
+            lk = h * (p.slope_l * x - 0.5 / x) - 1.5 * logx + p.c_l;
         }
-        double fp;
-        double u = newton(x, fp);  // saddle_point (src/pgm_saddle.c:235-244)
-        double t = u + p.half_z2;
-        double lphi = h * (p.log_cosh_z + cumulant0(u) - t * x) + p.log_sqrt_h2pi - 0.5 * log(fp);
+        // starting point of the saddle-point solve: large-argument form for small x, else the
+        // expansion about xl, else the reference's table
+        double u0;
+        const double d = x - p.xl;
+        if (x <= 0.25) {
+            u0 = table_guess(x);
+        }
+        else if (fabs(d) <= 0.5 * p.xl) {
+            u0 = fmin(-p.half_z2 + d * (p.a1 + p.a2 * d), kUMax - 1e-3);
+        }
+        else {
+            u0 = table_guess(x);
+        }
+        double f, fp;
+        const double u = solve(x, u0, f, fp);
+        const double t = u + p.half_z2;
+        const double lphi = h * (cumulant0(u, f) - t * x) - 0.5 * log(fp);
         if (log(r.uniform32()) + lk <= lphi) {
             s.acc = 0.25 * h * x;
             return true;
@@ -516,6 +657,9 @@ struct Saddle {
         return false;
     }
 };
+
+using SaddleFull = SaddleT<true>;
+using SaddleLeft = SaddleT<false>;
 
 // =========================================================================================
 // Normal approximation (h > 50) and truncated gamma convolution   (src/pgm_random.c)

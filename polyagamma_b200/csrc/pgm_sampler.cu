@@ -92,14 +92,9 @@ profile_end(double* ms, uint64_t* launches, int cap)
 // ---------------------------------------------------------------------------------------
 // operand addressing: scalar / contiguous / broadcast-strided
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void
-load_hz(const FillArgs& a, uint64_t g, double& h, double& z)
+__device__ __noinline__ void
+load_hz_strided(const FillArgs& a, uint64_t g, double& h, double& z)
 {
-    if (a.bc.ndim == 0) {
-        h = a.h ? a.h[g * a.h_stride] : a.h_scalar;
-        z = a.z ? a.z[g * a.z_stride] : a.z_scalar;
-        return;
-    }
     int64_t oh = 0, oz = 0;
     uint64_t rem = g;
     for (int d = a.bc.ndim - 1; d >= 0; --d) {
@@ -113,12 +108,23 @@ load_hz(const FillArgs& a, uint64_t g, double& h, double& z)
     z = a.z[oz];
 }
 
+__device__ __forceinline__ void
+load_hz(const FillArgs& a, uint64_t g, double& h, double& z)
+{
+    if (a.bc.ndim == 0) {
+        h = a.h ? a.h[g * a.h_stride] : a.h_scalar;
+        z = a.z ? a.z[g * a.z_stride] : a.z_scalar;
+        return;
+    }
+    load_hz_strided(a, g, h, z);
+}
+
 // nan_or_inf (src/pgm_random.c:137-141); true if h is not a valid shape
-__device__ __forceinline__ bool
+__host__ __device__ __forceinline__ bool
 invalid_h(double h, double& value)
 {
     if (!(h > 0.0)) {
-        value = nan("");
+        value = NAN;
         return true;
     }
     if (isinf(h)) {
@@ -129,32 +135,45 @@ invalid_h(double h, double& value)
 }
 
 // ---------------------------------------------------------------------------------------
-// bucketing pre-pass (hybrid)
+// bucketing pre-pass
 // ---------------------------------------------------------------------------------------
 constexpr int kBucketThreads = 256;
 constexpr int kBucketItems = 8;
 constexpr int kBucketTile = kBucketThreads * kBucketItems;  // elements per block
-constexpr int kNumBuckets = 4;                              // devroye, alternate, saddle, normal
 constexpr uint8_t kBucketNone = 255;
 
-__device__ __forceinline__ uint8_t
-bucket_of(int method)
+// bucket ids (also the order of the per-method lists inside the chunk's index list)
+enum : int { kBDevroye = 0, kBAlternate = 1, kBSaddleFull = 2, kBSaddleLeft = 3, kBNormal = 4, kBGamma = 5,
+             kNumBuckets = 6 };
+
+// ctl layout (uint32): [0..5] bucket counts, [8..13] list bases, [16..21] work counters
+constexpr int kCtlCount = 0, kCtlBase = 8, kCtlWork = 16, kCtlWords = 32;
+
+__host__ __device__ __forceinline__ int
+bucket_of(int method, double h, double z, bool compat)
 {
-    // kDevroye=1 -> 0, kAlternate=2 -> 1, kSaddle=3 -> 2, kNormal=5 -> 3
-    return method == kNormal ? 3 : (uint8_t)(method - 1);
+    switch (method) {
+        case kDevroye: return kBDevroye;
+        case kAlternate: return kBAlternate;
+        case kSaddle: return saddle_left_only(h, z, compat) ? kBSaddleLeft : kBSaddleFull;
+        case kNormal: return kBNormal;
+        default: return kBGamma;
+    }
 }
 
 // Thread t of warp w in block b owns elements  b*Tile + w*256 + k*32 + lane, k = 0..7.
+// `method` is the requested sampler (kHybrid: src/pgm_random.c:105-121 decides per element).
 __global__ void __launch_bounds__(kBucketThreads)
-classify_kernel(FillArgs a, uint32_t n, uint8_t* __restrict__ meth, uint32_t* __restrict__ block_counts)
+classify_kernel(FillArgs a, uint32_t n, int method, uint8_t* __restrict__ meth, uint32_t* __restrict__ block_counts)
 {
     __shared__ uint32_t s_cnt[kNumBuckets];
     if (threadIdx.x < kNumBuckets) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t wbase = blockIdx.x * kBucketTile + warp * (32 * kBucketItems);
-    uint32_t cnt[kNumBuckets] = {0, 0, 0, 0};
+    uint32_t cnt[kNumBuckets];
 #pragma unroll
+    for (int q = 0; q < kNumBuckets; ++q) cnt[q] = 0;
     for (int k = 0; k < kBucketItems; ++k) {
         uint32_t e = wbase + k * 32 + lane;
         uint8_t b = kBucketNone;
@@ -165,7 +184,8 @@ classify_kernel(FillArgs a, uint32_t n, uint8_t* __restrict__ meth, uint32_t* __
                 a.out[a.base + e] = bad;
             }
             else {
-                b = bucket_of(hybrid_select(h, z));
+                int m = (method == kHybrid) ? hybrid_select(h, z) : method;
+                b = (uint8_t)bucket_of(m, h, z, a.compat != 0);
             }
             meth[e] = b;
         }
@@ -182,8 +202,7 @@ classify_kernel(FillArgs a, uint32_t n, uint8_t* __restrict__ meth, uint32_t* __
     if (threadIdx.x < kNumBuckets) block_counts[blockIdx.x * kNumBuckets + threadIdx.x] = s_cnt[threadIdx.x];
 }
 
-// One block: exclusive scan over blocks for each bucket; totals and list bases.
-// ctl layout: [0..3] totals, [4..7] bases, [8..11] work counters (zeroed by the host memset)
+// One block: exclusive scan over blocks for each bucket; totals and list bases into ctl.
 __global__ void __launch_bounds__(1024)
 scan_kernel(const uint32_t* __restrict__ block_counts, uint32_t nblocks, uint32_t* __restrict__ block_offsets,
             uint32_t* __restrict__ ctl)
@@ -191,8 +210,10 @@ scan_kernel(const uint32_t* __restrict__ block_counts, uint32_t nblocks, uint32_
     __shared__ uint32_t s_part[1024][kNumBuckets];
     const uint32_t t = threadIdx.x;
     const uint32_t per = (nblocks + 1023) / 1024;
-    const uint32_t lo = t * per, hi = min(lo + per, nblocks);
-    uint32_t sum[kNumBuckets] = {0, 0, 0, 0};
+    const uint32_t lo = min(t * per, nblocks), hi = min(lo + per, nblocks);
+    uint32_t sum[kNumBuckets];
+#pragma unroll
+    for (int q = 0; q < kNumBuckets; ++q) sum[q] = 0;
     for (uint32_t b = lo; b < hi; ++b) {
 #pragma unroll
         for (int q = 0; q < kNumBuckets; ++q) sum[q] += block_counts[b * kNumBuckets + q];
@@ -200,7 +221,7 @@ scan_kernel(const uint32_t* __restrict__ block_counts, uint32_t nblocks, uint32_
 #pragma unroll
     for (int q = 0; q < kNumBuckets; ++q) s_part[t][q] = sum[q];
     __syncthreads();
-    // Hillis-Steele inclusive scan over the 1024 partials, all four buckets at once
+    // Hillis-Steele inclusive scan over the 1024 partials, all buckets at once
     for (uint32_t off = 1; off < 1024; off <<= 1) {
         uint32_t v[kNumBuckets];
 #pragma unroll
@@ -224,8 +245,8 @@ scan_kernel(const uint32_t* __restrict__ block_counts, uint32_t nblocks, uint32_
         uint32_t base = 0;
 #pragma unroll
         for (int q = 0; q < kNumBuckets; ++q) {
-            ctl[q] = s_part[1023][q];
-            ctl[4 + q] = base;
+            ctl[kCtlCount + q] = s_part[1023][q];
+            ctl[kCtlBase + q] = base;
             base += s_part[1023][q];
         }
     }
@@ -239,7 +260,9 @@ scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __r
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t wbase = blockIdx.x * kBucketTile + warp * (32 * kBucketItems);
     uint8_t m[kBucketItems];
-    uint32_t cnt[kNumBuckets] = {0, 0, 0, 0};
+    uint32_t cnt[kNumBuckets];
+#pragma unroll
+    for (int q = 0; q < kNumBuckets; ++q) cnt[q] = 0;
 #pragma unroll
     for (int k = 0; k < kBucketItems; ++k) {
         uint32_t e = wbase + k * 32 + lane;
@@ -255,7 +278,7 @@ scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __r
     uint32_t off[kNumBuckets];
 #pragma unroll
     for (int q = 0; q < kNumBuckets; ++q) {
-        uint32_t o = ctl[4 + q] + block_offsets[blockIdx.x * kNumBuckets + q];
+        uint32_t o = ctl[kCtlBase + q] + block_offsets[blockIdx.x * kNumBuckets + q];
         for (uint32_t w = 0; w < warp; ++w) o += s_warp[w][q];
         off[q] = o;
     }
@@ -273,6 +296,79 @@ scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __r
 }
 
 // ---------------------------------------------------------------------------------------
+// work description shared by the per-method kernels
+// ---------------------------------------------------------------------------------------
+// A bucket is either the identity range [0, count_imm) of the chunk (ctl == nullptr) or the
+// bucket-th sub-list of `list`, whose length and base live in ctl on the device.
+struct Bucket {
+    const uint32_t* list;
+    const uint32_t* ctl;
+    int bucket;
+    uint32_t count_imm;
+    double* params;  // record storage for this chunk (kMaxRecordFields doubles per element)
+    int uniform;     // 1: one record (position 0) serves every element (scalar h and z)
+};
+
+struct BucketView {
+    const uint32_t* list;
+    uint32_t count;
+    double* recs;     // field f of position p at recs[f * stride + p]
+    uint32_t stride;
+};
+
+__device__ __forceinline__ BucketView
+view_of(const Bucket& b)
+{
+    BucketView v;
+    v.list = b.list;
+    v.count = b.count_imm;
+    v.recs = b.params;
+    if (b.ctl) {
+        uint32_t base = b.ctl[kCtlBase + b.bucket];
+        v.count = b.ctl[kCtlCount + b.bucket];
+        v.list = b.list + base;
+        v.recs = b.params + (size_t)base * kMaxRecordFields;
+    }
+    v.stride = b.uniform ? 1u : v.count;
+    return v;
+}
+
+struct RecView {
+    const double* base;
+    uint32_t stride, pos;
+    __device__ __forceinline__ double operator[](int f) const { return base[(size_t)f * stride + pos]; }
+};
+
+// ---------------------------------------------------------------------------------------
+// setup kernel: one thread per element, no rejection loops
+// ---------------------------------------------------------------------------------------
+template <class M>
+__global__ void __launch_bounds__(256)
+setup_kernel(FillArgs a, Bucket b)
+{
+    const BucketView v = view_of(b);
+    const uint32_t nrec = b.uniform ? 1u : v.count;
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < nrec; pos += gridDim.x * blockDim.x) {
+        uint32_t e = v.list ? v.list[pos] : pos;
+        uint64_t g = a.base + e;
+        double h, z, bad;
+        load_hz(a, g, h, z);
+        double rec[M::kFields];
+        if (invalid_h(h, bad)) {
+            // only reachable on the identity range (classify_kernel filters invalid h itself)
+            if (!b.uniform) a.out[g] = bad;
+#pragma unroll
+            for (int f = 0; f < M::kFields; ++f) rec[f] = NAN;
+        }
+        else {
+            M::make_record(h, z, a.compat != 0, rec);
+        }
+#pragma unroll
+        for (int f = 0; f < M::kFields; ++f) v.recs[(size_t)f * v.stride + pos] = rec[f];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // persistent rejection-sampling kernel
 // ---------------------------------------------------------------------------------------
 constexpr int kPersistThreads = 256;
@@ -280,14 +376,12 @@ constexpr uint32_t kWorkBatch = 64;  // elements a warp reserves per atomic
 
 template <class M>
 __global__ void __launch_bounds__(kPersistThreads)
-persistent_kernel(FillArgs a, const uint32_t* __restrict__ list, const uint32_t* __restrict__ ctl, int bucket,
-                  uint32_t count_imm, uint32_t* __restrict__ counter)
+sample_kernel(FillArgs a, Bucket b, uint32_t* __restrict__ counter)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
-    // hybrid: this bucket's count and list base were written by scan_kernel
-    const uint32_t count = ctl ? ctl[bucket] : count_imm;
-    if (ctl) list += ctl[4 + bucket];
+    const BucketView v = view_of(b);
+    const uint32_t count = v.count;
     const bool compat = a.compat != 0;
 
     typename M::Par par;
@@ -302,36 +396,31 @@ persistent_kernel(FillArgs a, const uint32_t* __restrict__ list, const uint32_t*
         uint32_t need = __ballot_sync(0xffffffffu, !active);
         if (need != 0 && !(exhausted && wnext == wend)) {
             if (wnext == wend) {
-                uint32_t b = 0;
-                if (lane == 0) b = atomicAdd(counter, kWorkBatch);
-                b = __shfl_sync(0xffffffffu, b, 0);
-                if (b >= count) {
+                uint32_t w = 0;
+                if (lane == 0) w = atomicAdd(counter, kWorkBatch);
+                w = __shfl_sync(0xffffffffu, w, 0);
+                if (w >= count) {
                     exhausted = true;
                 }
                 else {
-                    wnext = b;
-                    wend = min(b + kWorkBatch, count);
+                    wnext = w;
+                    wend = min(w + kWorkBatch, count);
                 }
             }
             if (wnext < wend) {
                 uint32_t pos = wnext + __popc(need & lt);
                 if (!active && pos < wend) {
-                    uint32_t e = list ? list[pos] : pos;
+                    uint32_t e = v.list ? v.list[pos] : pos;
                     g = a.base + e;
-                    double h, z, bad;
-                    load_hz(a, g, h, z);
-                    if (invalid_h(h, bad)) {
-                        a.out[g] = bad;
-                    }
-                    else {
-                        M::setup(par, h, z, compat);
-                        M::begin(par, st, h, z, compat);
-                        if (M::empty(st)) {
-                            a.out[g] = 0.0;
-                        }
-                        else {
+                    RecView rec{v.recs, v.stride, b.uniform ? 0u : pos};
+                    double r0 = rec[0];
+                    if (r0 == r0) {  // NaN record: invalid h, already written by setup_kernel
+                        if (M::load(rec, par, st, compat)) {
                             rng.init(a.key, a.first_index + g);
                             active = true;
+                        }
+                        else {
+                            a.out[g] = 0.0;  // nothing to draw (devroye with floor(h) == 0)
                         }
                     }
                 }
@@ -353,13 +442,11 @@ persistent_kernel(FillArgs a, const uint32_t* __restrict__ list, const uint32_t*
 // ---------------------------------------------------------------------------------------
 template <int KIND>
 __global__ void __launch_bounds__(256)
-dense_kernel(FillArgs a, const uint32_t* __restrict__ list, const uint32_t* __restrict__ ctl, int bucket,
-             uint32_t count_imm)
+dense_kernel(FillArgs a, Bucket b)
 {
-    const uint32_t count = ctl ? ctl[bucket] : count_imm;
-    if (ctl) list += ctl[4 + bucket];
-    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < count; pos += gridDim.x * blockDim.x) {
-        uint32_t e = list ? list[pos] : pos;
+    const BucketView v = view_of(b);
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < v.count; pos += gridDim.x * blockDim.x) {
+        uint32_t e = v.list ? v.list[pos] : pos;
         uint64_t g = a.base + e;
         double h, z, bad;
         load_hz(a, g, h, z);
@@ -370,6 +457,14 @@ dense_kernel(FillArgs a, const uint32_t* __restrict__ list, const uint32_t* __re
         Rng rng;
         rng.init(a.key, a.first_index + g);
         a.out[g] = (KIND == kNormal) ? normal_approx_sample(rng, h, z) : gamma_conv_sample(rng, h, z);
+    }
+}
+
+__global__ void
+fill_value_kernel(double* __restrict__ out, uint64_t n, double value)
+{
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        out[i] = value;
     }
 }
 
@@ -390,7 +485,7 @@ check_h_kernel(const double* __restrict__ h, size_t n, int devroye, int* __restr
 // ---------------------------------------------------------------------------------------
 struct DeviceInfo {
     int sms = 0;
-    int blocks_per_sm[4] = {0, 0, 0, 0};  // devroye, alternate, saddle persistent kernels
+    int blocks_per_sm[4] = {0, 0, 0, 0};  // devroye, alternate, saddle-full, saddle-left sampling kernels
 };
 
 static DeviceInfo
@@ -402,10 +497,11 @@ device_info()
     DeviceInfo& d = cache[dev & 63];
     if (d.sms == 0) {
         cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[0], persistent_kernel<Devroye>, kPersistThreads, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[1], persistent_kernel<Alternate>, kPersistThreads, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[2], persistent_kernel<Saddle>, kPersistThreads, 0);
-        for (int i = 0; i < 3; ++i) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[0], sample_kernel<Devroye>, kPersistThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[1], sample_kernel<Alternate>, kPersistThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[2], sample_kernel<SaddleFull>, kPersistThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[3], sample_kernel<SaddleLeft>, kPersistThreads, 0);
+        for (int i = 0; i < 4; ++i) {
             if (d.blocks_per_sm[i] < 1) d.blocks_per_sm[i] = 1;
         }
         // stream-ordered scratch: keep freed blocks cached in the pool instead of returning
@@ -420,41 +516,50 @@ device_info()
 }
 
 static inline uint32_t
-persistent_grid(const DeviceInfo& d, int which, uint64_t count_hint)
+grid_for(uint64_t full, uint64_t count_hint, uint32_t threads)
 {
-    uint64_t full = (uint64_t)d.sms * d.blocks_per_sm[which];
-    uint64_t need = (count_hint + kPersistThreads - 1) / kPersistThreads;
+    uint64_t need = (count_hint + threads - 1) / threads;
     if (need < 1) need = 1;
     return (uint32_t)(need < full ? need : full);
 }
 
+// setup + persistent sampling of one bucket with method M (which: 0..3, kind: profiling id)
 template <class M>
 static void
-launch_persistent(const DeviceInfo& d, int which, const FillArgs& a, const uint32_t* list, const uint32_t* ctl,
-                  int bucket, uint32_t count_imm, uint64_t count_hint, uint32_t* counter, cudaStream_t s)
+launch_method(const DeviceInfo& d, int which, int kind, const FillArgs& a, const Bucket& b, uint64_t count_hint,
+              uint32_t* counter, cudaStream_t s)
 {
-    ScopedKernelTimer timer(kKindDevroye + which, s);
-    persistent_kernel<M><<<persistent_grid(d, which, count_hint), kPersistThreads, 0, s>>>(a, list, ctl, bucket,
-                                                                                          count_imm, counter);
-    count_launch(1);
+    {
+        ScopedKernelTimer timer(kKindSetup, s);
+        uint64_t nrec = b.uniform ? 1 : count_hint;
+        setup_kernel<M><<<grid_for((uint64_t)d.sms * 8, nrec, 256), 256, 0, s>>>(a, b);
+    }
+    {
+        ScopedKernelTimer timer(kind, s);
+        sample_kernel<M><<<grid_for((uint64_t)d.sms * d.blocks_per_sm[which], count_hint, kPersistThreads),
+                           kPersistThreads, 0, s>>>(a, b, counter);
+    }
+    count_launch(2);
 }
 
 template <int KIND>
 static void
-launch_dense(const DeviceInfo& d, const FillArgs& a, const uint32_t* list, const uint32_t* ctl, int bucket,
-             uint32_t count_imm, uint64_t count_hint, cudaStream_t s)
+launch_dense(const DeviceInfo& d, const FillArgs& a, const Bucket& b, uint64_t count_hint, cudaStream_t s)
 {
-    uint64_t need = (count_hint + 255) / 256;
-    uint64_t full = (uint64_t)d.sms * 8;
-    if (need < 1) need = 1;
     ScopedKernelTimer timer(KIND == kNormal ? kKindNormal : kKindGamma, s);
-    dense_kernel<KIND><<<(uint32_t)(need < full ? need : full), 256, 0, s>>>(a, list, ctl, bucket, count_imm);
+    dense_kernel<KIND><<<grid_for((uint64_t)d.sms * 8, count_hint, 256), 256, 0, s>>>(a, b);
     count_launch(1);
 }
 
-// Elements per pass through the pipeline.  Bounds the scratch (5 B/element + histograms)
+// Elements per pass through the pipeline.  Bounds the scratch (5 B + one record per element)
 // and keeps list indices in 32 bits.
-constexpr uint64_t kChunk = 1ull << 26;
+constexpr uint64_t kChunk = 1ull << 25;
+
+static inline size_t
+align256(size_t v)
+{
+    return (v + 255) & ~size_t(255);
+}
 
 int
 launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
@@ -463,50 +568,60 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     const int m = method & 0xff;
     a.compat = (method & 0x100) ? 1 : 0;
     if (m < kGamma || m > kHybrid) return -1;
+    const bool compat = a.compat != 0;
     DeviceInfo d = device_info();
     cudaError_t err;
 
     const bool scalar_params = (a.h == nullptr && a.z == nullptr && a.bc.ndim == 0);
-    int eff = m;
-    if (m == kHybrid && scalar_params) {
-        // src/pgm_random.c:105-121 applied once; invalid h is handled per element by every kernel
-        eff = (a.h_scalar > 0.0 && !isinf(a.h_scalar)) ? hybrid_select(a.h_scalar, a.z_scalar) : kDevroye;
-    }
-
-    if (eff != kHybrid) {
-        uint32_t* counter = nullptr;
-        const uint64_t nchunks = (n + kChunk - 1) / kChunk;
-        const bool persistent = (eff == kDevroye || eff == kAlternate || eff == kSaddle);
-        if (persistent) {
-            if ((err = cudaMallocAsync(&counter, nchunks * sizeof(uint32_t), s)) != cudaSuccess) return (int)err;
-            if ((err = cudaMemsetAsync(counter, 0, nchunks * sizeof(uint32_t), s)) != cudaSuccess) return (int)err;
+    if (scalar_params) {
+        // pgm_random_polyagamma_fill (src/pgm_random.c:158-170): one (h, z) for all n elements
+        double bad;
+        if (invalid_h(a.h_scalar, bad)) {
+            fill_value_kernel<<<grid_for((uint64_t)d.sms * 8, n, 256), 256, 0, s>>>(a.out + a.base, n, bad);
+            count_launch(1);
+            return (int)cudaGetLastError();
         }
+        const int eff = (m == kHybrid) ? hybrid_select(a.h_scalar, a.z_scalar) : m;
+        const int bk = bucket_of(eff, a.h_scalar, a.z_scalar, compat);
+        const uint64_t nchunks = (n + kChunk - 1) / kChunk;
+        char* ws = nullptr;
+        const size_t rec_bytes = align256(kMaxRecordFields * sizeof(double));
+        if ((err = cudaMallocAsync(&ws, rec_bytes + nchunks * sizeof(uint32_t), s)) != cudaSuccess) return (int)err;
+        double* params = (double*)ws;
+        uint32_t* counters = (uint32_t*)(ws + rec_bytes);
+        cudaMemsetAsync(counters, 0, nchunks * sizeof(uint32_t), s);
         const uint64_t base0 = a.base;
         for (uint64_t c = 0; c < nchunks; ++c) {
-            uint64_t off = c * kChunk;
-            uint32_t cn = (uint32_t)((n - off) < kChunk ? (n - off) : kChunk);
+            const uint64_t off = c * kChunk;
+            const uint32_t cn = (uint32_t)((n - off) < kChunk ? (n - off) : kChunk);
             a.base = base0 + off;
-            switch (eff) {
-                case kDevroye: launch_persistent<Devroye>(d, 0, a, nullptr, nullptr, 0, cn, cn, counter + c, s); break;
-                case kAlternate: launch_persistent<Alternate>(d, 1, a, nullptr, nullptr, 0, cn, cn, counter + c, s); break;
-                case kSaddle: launch_persistent<Saddle>(d, 2, a, nullptr, nullptr, 0, cn, cn, counter + c, s); break;
-                case kNormal: launch_dense<kNormal>(d, a, nullptr, nullptr, 0, cn, cn, s); break;
-                default: launch_dense<kGamma>(d, a, nullptr, nullptr, 0, cn, cn, s); break;
+            Bucket b{nullptr, nullptr, bk, cn, params, 1};
+            switch (bk) {
+                case kBDevroye: launch_method<Devroye>(d, 0, kKindDevroye, a, b, cn, counters + c, s); break;
+                case kBAlternate: launch_method<Alternate>(d, 1, kKindAlternate, a, b, cn, counters + c, s); break;
+                case kBSaddleFull: launch_method<SaddleFull>(d, 2, kKindSaddle, a, b, cn, counters + c, s); break;
+                case kBSaddleLeft: launch_method<SaddleLeft>(d, 3, kKindSaddleLeft, a, b, cn, counters + c, s); break;
+                case kBNormal: launch_dense<kNormal>(d, a, b, cn, s); break;
+                default: launch_dense<kGamma>(d, a, b, cn, s); break;
             }
         }
-        if (counter) cudaFreeAsync(counter, s);
+        cudaFreeAsync(ws, s);
         return (int)cudaGetLastError();
     }
 
-    // hybrid with per-element parameters: bucket by method, then one launch per method
+    // per-element parameters (fill2).  hybrid and saddle need the bucketing pre-pass (several
+    // kernels per chunk); devroye / alternate / gamma run on the identity range.
+    const bool bucketed = (m == kHybrid || m == kSaddle);
     const uint64_t cmax = n < kChunk ? n : kChunk;
     const uint32_t nblocks_max = (uint32_t)((cmax + kBucketTile - 1) / kBucketTile);
-    const size_t list_bytes = ((cmax * sizeof(uint32_t)) + 255) & ~size_t(255);
-    const size_t meth_bytes = (cmax + 255) & ~size_t(255);
-    const size_t hist_bytes = (((size_t)nblocks_max * kNumBuckets * sizeof(uint32_t)) + 255) & ~size_t(255);
-    const size_t ctl_bytes = 256;
+    const size_t list_bytes = bucketed ? align256(cmax * sizeof(uint32_t)) : 0;
+    const size_t meth_bytes = bucketed ? align256(cmax) : 0;
+    const size_t hist_bytes = bucketed ? align256((size_t)nblocks_max * kNumBuckets * sizeof(uint32_t)) : 0;
+    const size_t ctl_bytes = align256(kCtlWords * sizeof(uint32_t));
+    const size_t par_bytes = (m == kGamma) ? 0 : align256(cmax * kMaxRecordFields * sizeof(double));
     char* ws = nullptr;
-    if ((err = cudaMallocAsync(&ws, list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes, s)) != cudaSuccess) {
+    if ((err = cudaMallocAsync(&ws, list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes + par_bytes, s)) !=
+        cudaSuccess) {
         return (int)err;
     }
     uint32_t* list = (uint32_t*)ws;
@@ -514,16 +629,26 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     uint32_t* block_counts = (uint32_t*)(ws + list_bytes + meth_bytes);
     uint32_t* block_offsets = (uint32_t*)(ws + list_bytes + meth_bytes + hist_bytes);
     uint32_t* ctl = (uint32_t*)(ws + list_bytes + meth_bytes + 2 * hist_bytes);
+    double* params = (double*)(ws + list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes);
 
     const uint64_t base0 = a.base;
     for (uint64_t off = 0; off < n; off += kChunk) {
-        uint32_t cn = (uint32_t)((n - off) < kChunk ? (n - off) : kChunk);
-        uint32_t nblocks = (cn + kBucketTile - 1) / kBucketTile;
+        const uint32_t cn = (uint32_t)((n - off) < kChunk ? (n - off) : kChunk);
         a.base = base0 + off;
         cudaMemsetAsync(ctl, 0, ctl_bytes, s);
+        if (!bucketed) {
+            Bucket b{nullptr, nullptr, 0, cn, params, 0};
+            switch (m) {
+                case kDevroye: launch_method<Devroye>(d, 0, kKindDevroye, a, b, cn, ctl + kCtlWork, s); break;
+                case kAlternate: launch_method<Alternate>(d, 1, kKindAlternate, a, b, cn, ctl + kCtlWork, s); break;
+                default: launch_dense<kGamma>(d, a, b, cn, s); break;
+            }
+            continue;
+        }
+        const uint32_t nblocks = (cn + kBucketTile - 1) / kBucketTile;
         {
             ScopedKernelTimer timer(kKindClassify, s);
-            classify_kernel<<<nblocks, kBucketThreads, 0, s>>>(a, cn, meth, block_counts);
+            classify_kernel<<<nblocks, kBucketThreads, 0, s>>>(a, cn, m, meth, block_counts);
         }
         {
             ScopedKernelTimer timer(kKindScan, s);
@@ -534,12 +659,16 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
             scatter_kernel<<<nblocks, kBucketThreads, 0, s>>>(meth, cn, block_offsets, ctl, list);
         }
         count_launch(3);
-        // ctl[q] = count and ctl[4+q] = list base of bucket q stay on the device: the method
-        // kernels read them there, so the host never waits for the histogram.
-        launch_persistent<Devroye>(d, 0, a, list, ctl, 0, 0, cn, ctl + 8, s);
-        launch_persistent<Alternate>(d, 1, a, list, ctl, 1, 0, cn, ctl + 9, s);
-        launch_persistent<Saddle>(d, 2, a, list, ctl, 2, 0, cn, ctl + 10, s);
-        launch_dense<kNormal>(d, a, list, ctl, 3, 0, cn, s);
+        // counts and list bases stay on the device: the method kernels read them there, so the
+        // host never waits for the histogram (empty buckets cost one near-empty launch)
+        auto bucket = [&](int q) { return Bucket{list, ctl, q, 0, params, 0}; };
+        launch_method<SaddleFull>(d, 2, kKindSaddle, a, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s);
+        launch_method<SaddleLeft>(d, 3, kKindSaddleLeft, a, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s);
+        if (m == kHybrid) {
+            launch_method<Alternate>(d, 1, kKindAlternate, a, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s);
+            launch_method<Devroye>(d, 0, kKindDevroye, a, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s);
+            launch_dense<kNormal>(d, a, bucket(kBNormal), cn, s);
+        }
     }
     cudaFreeAsync(ws, s);
     return (int)cudaGetLastError();
