@@ -42,7 +42,17 @@ WORKLOAD = "cfg4: fill2 hybrid, h~U[0.1,200], z~U[-50,50] (BASELINE.json configs
 # Provenance: ncu `smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on.sum` of the kernels
 # in profiles/ divided by the elements of that launch -- see DESIGN.md "Roofline accounting";
 # SURVEY 8(d)'s nominal figures are kept beside them there.
-FLOPS_PER_ELEMENT = {"devroye": 1.1e3, "alternate": 4.0e3, "saddle": 9.0e3, "normal": 4.0e2, "gamma": 6.0e4}
+FLOPS_PER_ELEMENT = {"devroye": 6.0e2, "alternate": 1.5e3, "alternate_left": 6.0e2, "setup_alternate_left": 2.0, "saddle": 2.0e3, "saddle_left": 7.0e2, "saddle_far": 5.0e2,
+                     "normal": 1.45e2, "gamma": 6.0e4, "setup_devroye": 4.0e2, "setup_alternate": 2.5e3,
+                     "setup_saddle": 5.0e3, "setup_saddle_left": 4.5e2, "setup_saddle_far": 3.0e2}
+KERNEL_NAMES = {"devroye": "sample_kernel<Devroye>", "alternate": "sample_kernel<Alternate>",
+                "alternate_left": "sample_kernel<AlternateLeft>", "setup_alternate_left": "setup_kernel<AlternateLeft>",
+                "saddle": "sample_kernel<SaddleFull>", "saddle_left": "sample_kernel<SaddleLeft>",
+                "saddle_far": "sample_kernel<SaddleFar>",
+                "normal": "dense_kernel<normal>", "gamma": "dense_kernel<gamma>",
+                "setup_devroye": "setup_kernel<Devroye>", "setup_alternate": "setup_kernel<Alternate>",
+                "setup_saddle": "setup_kernel<SaddleFull>", "setup_saddle_left": "setup_kernel<SaddleLeft>",
+                "setup_saddle_far": "setup_kernel<SaddleFar>"}
 BYTES_PER_ELEMENT = 24 + 5  # h, z in + out (+ 1 B method id and 4 B list index written and read once)
 
 
@@ -266,17 +276,27 @@ def main():
     devroye = ~normal & ~saddle & ((h == 1) | ((h == torch.floor(h)) & (z <= 1)))
     mix = {"normal": int(normal.sum()), "saddle": int(saddle.sum()), "devroye": int(devroye.sum())}
     mix["alternate"] = n - sum(mix.values())
+    left_mask = saddle & (h * (1.0 + 0.125 * z.abs()) >= 22.0)
+    saddle_far_count = int((left_mask & (z.abs() >= 8.0)).sum())
+    saddle_left_count = int(left_mask.sum()) - saddle_far_count
+    alt_left_count = int((~normal & ~saddle & ~devroye & (z.abs() >= 14.0)).sum())
+    del left_mask
     del normal, saddle, devroye
-    sampler_kinds = ("devroye", "alternate", "saddle", "normal", "gamma")
-    dom = max(sampler_kinds, key=lambda k: kernels[k][0])
+    # saddle elements whose right envelope piece is unreachable run the left-only kernels
+    left, far = saddle_left_count, saddle_far_count
+    units = {"devroye": mix["devroye"], "alternate": mix["alternate"] - alt_left_count,
+             "alternate_left": alt_left_count, "saddle": mix["saddle"] - left - far,
+             "saddle_left": left, "saddle_far": far, "normal": mix["normal"], "gamma": 0}
+    units.update({"setup_" + k: units[k] for k in ("devroye", "alternate", "alternate_left", "saddle", "saddle_left",
+                                                    "saddle_far")})
+    dom = max(units, key=lambda k: kernels[k][0])
     dom_ms, dom_launches = kernels[dom]
     per_launch_s = dom_ms * 1e-3 / max(dom_launches, 1)
-    units_per_launch = mix.get(dom, 0) * args.steps / max(dom_launches, 1)
+    units_per_launch = units[dom] * args.steps / max(dom_launches, 1)
     achieved = units_per_launch * FLOPS_PER_ELEMENT[dom] / per_launch_s / 1e12
     total_kernel_ms = sum(v[0] for v in kernels.values())
     roofline = {
-        "bound": "fp64", "kernel": f"persistent_kernel<{dom}>" if dom in ("devroye", "alternate", "saddle")
-        else f"dense_kernel<{dom}>",
+        "bound": "fp64", "kernel": KERNEL_NAMES[dom],
         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
         "peak_source": "DFMA microbenchmark (pgm_cuda_fp64_peak_tflops) run in this process",
         "flops_per_unit": FLOPS_PER_ELEMENT[dom], "units_per_launch": units_per_launch,

@@ -116,10 +116,11 @@ uint64_t pgm_cuda_launch_count(void);
 /* Per-kernel device time, for roofline accounting.  Between _begin and _end every kernel this
  * library launches is bracketed by CUDA events on its own stream; _end synchronises those
  * events and returns, per kernel kind, the summed milliseconds and the launch count.
- * Kinds: 0 classify, 1 scan, 2 scatter, 3 devroye, 4 alternate, 5 saddle (both envelope
- * pieces), 6 normal, 7 gamma, 8 density, 9 per-element setup (all methods), 10 saddle (left
- * piece only).  `cap` = length of both output arrays (>= 11). */
-#define PGM_CUDA_NUM_KERNEL_KINDS 11
+ * Kinds: 0 classify, 1 scan, 2 scatter; sampling kernels 3 devroye, 4 alternate, 5 saddle (both
+ * envelope pieces), 6 saddle-left (left piece only, |z| < 8), 7 saddle-far (left piece, |z| >= 8),
+ * 8 alternate-left (left piece only, |z| >= 14); 9 normal, 10 gamma, 11 density; per-element
+ * setup kernels 12..17 in the order of 3..8.  `cap` = length of both output arrays (>= 18). */
+#define PGM_CUDA_NUM_KERNEL_KINDS 18
 void pgm_cuda_profile_begin(void);
 int pgm_cuda_profile_end(double* ms, uint64_t* launches, int cap);
 /* FP64 (DFMA) peak of the current device in TFLOP/s, measured by a register-resident FMA

@@ -114,8 +114,9 @@ def launch_count() -> int:
     return int(lib().pgm_cuda_launch_count())
 
 
-KERNEL_KINDS = ("classify", "scan", "scatter", "devroye", "alternate", "saddle", "normal", "gamma", "density",
-                "setup", "saddle_left")
+_METHOD_KERNELS = ("devroye", "alternate", "saddle", "saddle_left", "saddle_far", "alternate_left")
+KERNEL_KINDS = (("classify", "scan", "scatter") + _METHOD_KERNELS + ("normal", "gamma", "density") +
+                tuple("setup_" + k for k in _METHOD_KERNELS))
 
 
 def profile_begin() -> None:

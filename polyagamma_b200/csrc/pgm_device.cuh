@@ -32,14 +32,10 @@ philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-#ifdef __CUDA_ARCH__
-        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-#else
+        // one 32x32->64 multiply per half-round (IMAD.WIDE.U32 on the device)
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
         uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
-#endif
         uint32_t n0 = hi1 ^ c1 ^ k0;
         uint32_t n2 = hi0 ^ c3 ^ k1;
         c0 = n0;
@@ -65,7 +61,10 @@ derive_call_key(uint64_t seed, uint64_t offset)
 // One private stream per output element: words of Philox(call key, ctr = (idx, block, 0)),
 // block = 0, 1, 2, ..., consumed strictly in order.  The four buffered words live in
 // registers and are shifted down on every draw (no local-memory indexing).
-struct Rng {
+// OUTLINE: keep ONE copy of the block function per kernel (persistent samplers: many call sites,
+// instruction-cache bound) or inline it (dense kernels with a single draw site).
+template <bool OUTLINE>
+struct RngT {
     uint32_t k0, k1, i0, i1, blk;
     uint32_t b0, b1, b2, b3;
     int left;
@@ -80,16 +79,25 @@ struct Rng {
         left = 0;
     }
 
+    // One shared copy of the block function per kernel: u32() has many call sites in the
+    // samplers and the persistent kernels live or die by their instruction-cache footprint.
+    __device__ __forceinline__ void refill_body()
+    {
+        b0 = i0;
+        b1 = i1;
+        b2 = blk;
+        b3 = 0;
+        philox4x32_10(b0, b1, b2, b3, k0, k1);
+        ++blk;
+        left = 4;
+    }
+    __device__ __noinline__ void refill_outlined() { refill_body(); }
+
     __device__ __forceinline__ uint32_t u32()
     {
         if (left == 0) {
-            b0 = i0;
-            b1 = i1;
-            b2 = blk;
-            b3 = 0;
-            philox4x32_10(b0, b1, b2, b3, k0, k1);
-            ++blk;
-            left = 4;
+            if (OUTLINE) refill_outlined();
+            else refill_body();
         }
         uint32_t w = b0;
         b0 = b1;
@@ -231,9 +239,13 @@ log_upper_gamma(double p, double x, bool normalized)
     return normalized ? lq : lq + lg;
 }
 
+using RngOutlined = RngT<true>;
+using RngInline = RngT<false>;
+
 // random_left_bounded_gamma (src/pgm_common.h:126-157): X ~ Gamma(a, rate b) | X > t
+template <class R>
 __device__ inline double
-left_bounded_gamma(Rng& r, double a, double b, double t)
+left_bounded_gamma(R& r, double a, double b, double t)
 {
     double x;
     if (a > 1.0) {  // Dagpunar (1978)

@@ -57,15 +57,13 @@ enum : int {
     kKindClassify = 0,
     kKindScan = 1,
     kKindScatter = 2,
+    // sampling kernels: + 0 devroye, 1 alternate, 2 saddle, 3 saddle-left, 4 saddle-far, 5 alternate-left
     kKindDevroye = 3,
-    kKindAlternate = 4,
-    kKindSaddle = 5,
-    kKindNormal = 6,
-    kKindGamma = 7,
-    kKindDensity = 8,
-    kKindSetup = 9,
-    kKindSaddleLeft = 10,
-    kNumKinds = 11
+    kKindNormal = 9,
+    kKindGamma = 10,
+    kKindDensity = 11,
+    kKindSetup = 12,  // setup kernels, same order as the sampling kernels
+    kNumKinds = 18
 };
 
 class ScopedKernelTimer {

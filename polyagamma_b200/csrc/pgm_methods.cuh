@@ -28,10 +28,20 @@ namespace pgm {
 
 constexpr int kMaxRecordFields = 10;
 
+// Which sampling kernels keep a single out-of-line copy of the Philox block function (bit i =
+// method i in launch order: 0 devroye, 1 alternate, 2 saddle-full, 3 saddle-left, 4 saddle-far,
+// 5 alternate-left, 6 gamma).  Chosen per kernel by measurement (profiles/README.md).
+#ifndef PGM_RNG_OUTLINE_MASK
+#define PGM_RNG_OUTLINE_MASK 0x3e
+#endif
+template <int BIT>
+using RngFor = RngT<((PGM_RNG_OUTLINE_MASK >> BIT) & 1) != 0>;
+
 // =========================================================================================
 // Devroye: exact J*(1, z), summed floor(h) times            (src/pgm_devroye.c)
 // =========================================================================================
 struct Devroye {
+    using Rng = RngFor<0>;
     static constexpr double T = 0.64;
     static constexpr int kFields = 4;  // w, K, zz, count
 
@@ -182,6 +192,7 @@ static __constant__ double c_trunc_f[25] = {
     7.473186206, 7.734284136, 7.995175158, 8.255882407};
 
 struct Alternate {
+    using Rng = RngFor<1>;
     // h, zz, then (w_right, lgamma(h)) of the first piece and of the remainder piece
     static constexpr int kFields = 6;
 
@@ -390,6 +401,122 @@ struct Alternate {
     }
 };
 
+// Alternate elements whose right (truncated gamma) piece is unreachable: for |z| >= 14 its proposal
+// mass is below 2^-33 for every h <= 4 (tools/alternate_right_weight.py), so the 32-bit mixture
+// uniform always selects the truncated inverse-Gaussian; and since h/zz <= 4/7 < t(h) that draw is
+// always the Michael-Schucany-Haas branch.  No erfc, lgamma or incomplete gamma is ever needed:
+// the record is just (h, zz).
+__host__ __device__ __forceinline__ bool
+alternate_left_only(double z)
+{
+    return fabs(z) >= 14.0;
+}
+
+struct AlternateLeft {
+    using Rng = RngFor<5>;
+    static constexpr int kFields = 2;  // h, zz
+
+    struct Par {
+        double h, zz, z2, t, half_h2, hlog2, h_z, h_z2;
+    };
+    struct State {
+        double acc;
+        double h_rem;
+        double chunk;
+    };
+
+    static __device__ __forceinline__ void make_record(double h, double z, bool, double* rec)
+    {
+        rec[0] = h;
+        rec[1] = 0.5 * fabs(z);
+    }
+
+    static __device__ __forceinline__ void set_piece(Par& p, double h, double zz)
+    {
+        p.h = h;
+        p.zz = zz;
+        p.t = Alternate::trunc_point(h);
+        p.half_h2 = 0.5 * h * h;
+        p.hlog2 = h * kLog2;
+        p.z2 = zz * zz;
+        p.h_z = h / zz;
+        p.h_z2 = p.h_z * p.h_z;
+    }
+
+    template <class Rec>
+    static __device__ __forceinline__ bool load(const Rec& rec, Par& p, State& s, bool)
+    {
+        double h = rec[0], zz = rec[1];
+        s.acc = 0.0;
+        if (h > 4.0) {
+            s.chunk = (h >= 5.0) ? 4.0 : 3.0;
+            s.h_rem = h;
+            set_piece(p, s.chunk, zz);
+        }
+        else {
+            s.chunk = 0.0;
+            s.h_rem = 0.0;
+            set_piece(p, h, zz);
+        }
+        return true;
+    }
+
+    // random_jacobi_star (src/pgm_alternate.c:229-263), left piece only
+    static __device__ __forceinline__ bool step(Par& p, State& s, Rng& r, bool)
+    {
+        (void)r.uniform32();  // mixture draw: always the left piece here
+        double x;
+        do {
+            double y = r.normal();
+            double w = p.h_z + 0.5 * y * y / p.z2;
+            x = p.h_z2 / (w + sqrt(fmax(w * w - p.h_z2, 0.0)));
+            if (r.uniform_co() * (p.h_z + x) > p.h_z) {
+                x = p.h_z2 / x;
+            }
+        } while (x >= p.t);
+        const double logx = log(x);
+        const double base = p.hlog2 - kLs2Pi - 1.5 * logx;
+        const double inv2x = 0.5 / x;
+        // k(x) = a_0(x) on the left of t: u = U * a_0
+        double a_prev = p.h * exp(base - p.h * p.h * inv2x);
+        const double u = r.uniform32() * a_prev;
+        double c = 1.0;
+        double sum = a_prev;
+        bool accept = false;
+        for (int n = 1; n < 2000; ++n) {
+            double tn = 2.0 * n + p.h;
+            c *= (n - 1.0 + p.h) / n;
+            double a = c * tn * exp(base - tn * tn * inv2x);
+            if (n & 1) {
+                sum -= a;
+                if (u <= sum) {
+                    accept = true;
+                    break;
+                }
+            }
+            else {
+                sum += a;
+                if (a <= a_prev && u > sum) break;
+            }
+            a_prev = a;
+        }
+        if (!accept) return false;
+        s.acc += x;
+        if (s.chunk > 0.0) {
+            s.h_rem -= s.chunk;
+            if (!(s.h_rem > 4.0)) {
+                double hr = s.h_rem;
+                s.chunk = 0.0;
+                s.h_rem = 0.0;
+                set_piece(p, hr, p.zz);
+            }
+            return false;
+        }
+        s.acc *= 0.25;
+        return true;
+    }
+};
+
 // =========================================================================================
 // Saddle-point approximation                                 (src/pgm_saddle.c)
 // =========================================================================================
@@ -397,18 +524,19 @@ struct Alternate {
 // FULL = false is the specialisation for elements whose right-hand (truncated gamma) envelope
 // piece carries less than 2^-33 of the proposal mass: the 32-bit mixture uniform can then never
 // select it, so neither the right tangent nor the incomplete gamma function is needed and the
-// per-proposal code has a single branch-free path.  saddle_left_only() is the (h, z) rule.
+// per-proposal code has a single branch-free path.  saddle_mode() is the (h, z) rule.
 namespace saddle {
 
 constexpr double kUMax = 1.2337005501361697;  // just below pi^2 / 8, the pole of tan
 
 // K'(u), K''(u), K'''(u) of the cumulant generating function (cumulant_prime,
 // src/pgm_saddle.c:100-107, with exact tan / tanh instead of the rational tanh_x :56-74)
+template <bool NEG = false>
 __device__ __forceinline__ void
 kprime3(double u, double& f, double& fp, double& fpp)
 {
     double s2 = 2.0 * u;
-    if (fabs(s2) < 1e-4) {
+    if (!NEG && fabs(s2) < 1e-4) {
         double g = 1.0 / 3.0 + s2 * (2.0 / 15.0 + s2 * (17.0 / 315.0));
         f = 1.0 + s2 * g;
         fp = f * f - g;
@@ -418,8 +546,8 @@ kprime3(double u, double& f, double& fp, double& fpp)
     double a = fabs(s2);
     double rs = rsqrt(a);
     double s = a * rs;
-    double inv = (s2 > 0.0) ? rs * rs : -(rs * rs);
-    f = ((s2 > 0.0) ? tan(s) : tanh(s)) * rs;
+    double inv = (!NEG && s2 > 0.0) ? rs * rs : -(rs * rs);
+    f = ((!NEG && s2 > 0.0) ? tan(s) : tanh(s)) * rs;
     double t = (1.0 - f) * inv;
     fp = f * f + t;
     fpp = 2.0 * f * fp - fp * inv - 2.0 * t * inv;
@@ -449,13 +577,21 @@ cumulant0(double u, double f)
 
 // select_starting_guess (src/pgm_saddle.c:119-125); for x <= 0.25 the large-argument solution of
 // tanh(s)/s = x replaces the constant -9
+// Large-argument solution of tanh(s)/s = x: two fixed-point passes of s = tanh(s)/x from s = 1/x
+// written out with tanh s = 1 - 2 e^{-2s} + 2 e^{-4s}; relative residual < 1e-9 for x <= 0.2.
+__device__ __forceinline__ double
+asymptotic_guess(double x)
+{
+    const double xi = 1.0 / x;
+    const double e = exp(-2.0 * xi);
+    const double s = (1.0 - 2.0 * e + e * e * (2.0 - 8.0 * xi)) * xi;
+    return -0.5 * s * s;
+}
+
 __device__ __forceinline__ double
 table_guess(double x)
 {
-    if (x <= 0.25) {
-        double s = (1.0 - 2.0 * exp(-2.0 / x)) / x;
-        return -0.5 * s * s;
-    }
+    if (x <= 0.25) return asymptotic_guess(x);
     return x <= 0.5 ? -1.78 : x <= 1.0 ? -0.147 : x <= 1.5 ? 0.345 : x <= 2.5 ? 0.72 : x <= 4.0 ? 0.95 : 1.15;
 }
 
@@ -463,23 +599,46 @@ table_guess(double x)
 // Halley's iteration (uses K''', which is free once K' and K'' are known) falls back to a
 // Newton step when its denominator is not positive.  On return f = K'(u), fp = K''(u) were
 // evaluated AT the returned u.
+template <bool NEG = false>
 __device__ __forceinline__ double
 solve(double x, double u, double& f, double& fp)
 {
     double fpp;
     for (int n = 0; n < 30; ++n) {
-        kprime3(u, f, fp, fpp);
+        kprime3<NEG>(u, f, fp, fpp);
         double g = f - x;
         if (fabs(g) <= 1e-9 * x || !(fp > 1e-300)) return u;
         double den = 2.0 * fp * fp - g * fpp;
         double du = (den > 0.0) ? 2.0 * g * fp / den : g / fp;
         double un = u - du;
         if (un >= kUMax) un = 0.5 * (u + kUMax);  // never step onto / over the pole
+        if (NEG && un > -1e-3) un = 0.5 * (u - 1e-3);
         if (un == u) return u;
         u = un;
     }
-    kprime3(u, f, fp, fpp);
+    kprime3<NEG>(u, f, fp, fpp);
     return u;
+}
+
+// Starting points for the two per-(h, z) solves of the setup, K'(u) = 2.75 xl and K'(u) = 3 xl with
+// xl = tanh(zz)/zz: both are functions of zz alone, tabulated on zz in [0, kGuessZMax] (step
+// 1/16, filled once per device by init_guess_tables_kernel with the solver itself) and
+// interpolated linearly -- error ~1e-4, so one Halley step lands below the 1e-9 tolerance and
+// every lane of a warp takes the same two evaluations.
+constexpr double kGuessZMax = 11.0;
+constexpr int kGuessPerUnit = 16;
+constexpr int kGuessN = (int)(kGuessZMax * kGuessPerUnit) + 2;
+static __device__ double g_guess_uc[kGuessN];
+static __device__ double g_guess_ur[kGuessN];
+
+__device__ __forceinline__ double
+table_interp(const double* tab, double zz)
+{
+    double pos = zz * kGuessPerUnit;
+    int i = (int)pos;
+    double fr = pos - i;
+    double a = __ldg(tab + i), b = __ldg(tab + i + 1);
+    return a + (b - a) * fr;
 }
 
 // invgauss_logcdf (src/pgm_saddle.c:282-292)
@@ -499,14 +658,25 @@ invgauss_logcdf(double x, double mu, double lambda)
 // Elements of the saddle method whose right envelope piece is unreachable (weight < 2^-33, see
 // tools/saddle_right_weight.py for the map of log10 w_right over (h, |z|/2)).  Only used with
 // the consistent envelope; ref_compat keeps the reference's (much larger) right weight.
-__host__ __device__ __forceinline__ bool
-saddle_left_only(double h, double z, bool compat)
+// A further split keeps warps homogeneous: for |z| >= 8 (zz >= 4) the proposals sit around
+// xl = tanh(zz)/zz <= 1/4, where the large-argument starting point solves K'(u) = x in one or two
+// evaluations, and u < 0 always (x < xc < 1: tanh branch only); for smaller |z| the solve starts
+// from the Taylor expansion and takes two or three.  Mixing both in a warp left half of its lanes
+// idle (ncu: 17 of 32 lanes active).
+enum : int { kSaddleFar = 0, kSaddleLeft = 1, kSaddleFull = 2 };
+
+__host__ __device__ __forceinline__ int
+saddle_mode(double h, double z, bool compat)
 {
-    return !compat && h * (1.0 + 0.125 * fabs(z)) >= 22.0;
+    if (compat || !(h * (1.0 + 0.125 * fabs(z)) >= 22.0)) return kSaddleFull;
+    return fabs(z) >= 8.0 ? kSaddleFar : kSaddleLeft;
 }
 
-template <bool FULL>
+template <int MODE>
 struct SaddleT {
+    using Rng = RngFor<(MODE == kSaddleFull ? 2 : MODE == kSaddleLeft ? 3 : 4)>;
+    static constexpr bool FULL = (MODE == kSaddleFull);
+    static constexpr bool FAR = (MODE == kSaddleFar);
     // h, zz, xl, c_l, a1, a2 [, w_left, c_r, slope_r]
     static constexpr int kFields = FULL ? 9 : 6;
 
@@ -524,43 +694,54 @@ struct SaddleT {
         using namespace saddle;
         double zz = 0.5 * fabs(z);
         if (!(zz > 0.0)) zz = 0.0;
-        double xl, logxl, half_z2, log_cosh_z;
+        double xl, half_z2, log_cosh_z;
         if (zz > 0.0) {
-            double e = exp(-2.0 * zz);
+            const double e = exp(-2.0 * zz);
             xl = (1.0 - e) / ((1.0 + e) * zz);  // tanh(zz) / zz
-            logxl = log(xl);
             half_z2 = 0.5 * zz * zz;
-            log_cosh_z = zz + log1p(e) - kLog2;
+            // log cosh(zz) = zz - log 2 + log1p(e^{-2 zz})
+            log_cosh_z = zz - kLog2 + (e < 2.5e-3 ? e * (1.0 - e * (0.5 - e * (1.0 / 3.0 - 0.25 * e))) : log1p(e));
         }
         else {
             xl = 1.0;
-            logxl = 0.0;
             half_z2 = 0.0;
             log_cosh_z = 0.0;
         }
         const double xc = 2.75 * xl;
         const double xc_inv = 1.0 / xc;
-        const double xl_inv = 1.0 / xl;
+        const double xl_inv = 2.75 * xc_inv;
         double f, fp_c;
-        (void)solve(xc, table_guess(xc), f, fp_c);
-        const double alpha_r = fp_c * xc_inv * xc_inv;  // K''(u(xc)) / xc^2
+        const bool tabulated = zz < kGuessZMax;
+        (void)solve<FAR>(xc, tabulated ? table_interp(g_guess_uc, zz) : table_guess(xc), f, fp_c);
+        const double alpha_r = fp_c * xc_inv * xc_inv;  // K2(u(xc)) / xc^2, K2 = second derivative
         const double alpha_l = xc_inv * alpha_r;
         const double icpt_l = -0.5 * xc_inv + xl_inv;  // cumulant(ul) = 0, src/pgm_saddle.c:216
-        // second-order expansion of u(x) about x = xl, where u = -zz^2/2 exactly:
-        // du/dx = 1 / K'', d2u/dx2 = -K''' / K''^3
-        double f_l, fp_l, fpp_l;
-        kprime3(-half_z2, f_l, fp_l, fpp_l);
+        // second-order expansion of u(x) about x = xl, where u = -zz^2/2 and K1(u) = xl exactly:
+        // du/dx = 1 / K2, d2u/dx2 = -K3 / K2^3  (K1, K2, K3 = derivatives of the cumulant)
+        double fp_l, fpp_l;
+        if (zz * zz < 1e-4) {
+            double f_l;
+            kprime3(-half_z2, f_l, fp_l, fpp_l);
+        }
+        else {
+            const double inv = -1.0 / (zz * zz);
+            const double t = (1.0 - xl) * inv;
+            fp_l = xl * xl + t;
+            fpp_l = 2.0 * xl * fp_l - fp_l * inv - 2.0 * t * inv;
+        }
+        const double a1 = 1.0 / fp_l;
         rec[0] = h;
         rec[1] = zz;
         rec[2] = xl;
         // constant part of  log k_l(x) - log phi(x)  (bounding_kernel :250-263, saddle_point :235-244)
         rec[3] = 0.5 * h * xc_inv + h * icpt_l - 0.5 * log(alpha_l) - h * log_cosh_z;
-        rec[4] = 1.0 / fp_l;
-        rec[5] = -0.5 * fpp_l / (fp_l * fp_l * fp_l);
+        rec[4] = a1;
+        rec[5] = -0.5 * fpp_l * a1 * a1 * a1;
         if (FULL) {
+            const double logxl = log(xl);
             const double xr = 3.0 * xl;
             double fp_r;
-            double ur = solve(xr, table_guess(xr), f, fp_r);
+            double ur = solve(xr, tabulated ? table_interp(g_guess_ur, zz) : table_guess(xr), f, fp_r);
             const double tr = ur + half_z2;
             const double logxc = 1.0116009116784799 + logxl;  // log(2.75)
             const double slope_r = -tr - 1.0 / xr;
@@ -638,16 +819,17 @@ struct SaddleT {
         double u0;
         const double d = x - p.xl;
         if (x <= 0.25) {
-            u0 = table_guess(x);
+            u0 = asymptotic_guess(x);
         }
         else if (fabs(d) <= 0.5 * p.xl) {
-            u0 = fmin(-p.half_z2 + d * (p.a1 + p.a2 * d), kUMax - 1e-3);
+            u0 = -p.half_z2 + d * (p.a1 + p.a2 * d);
+            u0 = FAR ? fmin(u0, -1e-3) : fmin(u0, kUMax - 1e-3);
         }
         else {
             u0 = table_guess(x);
         }
         double f, fp;
-        const double u = solve(x, u0, f, fp);
+        const double u = solve<FAR>(x, u0, f, fp);
         const double t = u + p.half_z2;
         const double lphi = h * (cumulant0(u, f) - t * x) - 0.5 * log(fp);
         if (log(r.uniform32()) + lk <= lphi) {
@@ -658,16 +840,19 @@ struct SaddleT {
     }
 };
 
-using SaddleFull = SaddleT<true>;
-using SaddleLeft = SaddleT<false>;
+using SaddleFull = SaddleT<kSaddleFull>;
+using SaddleLeft = SaddleT<kSaddleLeft>;
+using SaddleFar = SaddleT<kSaddleFar>;
+
 
 // =========================================================================================
 // Normal approximation (h > 50) and truncated gamma convolution   (src/pgm_random.c)
 // =========================================================================================
 
 // random_polyagamma_normal_approx (src/pgm_random.c:47-66), cancellation-free moments
+template <class R>
 __device__ __forceinline__ double
-normal_approx_sample(Rng& r, double h, double z)
+normal_approx_sample(R& r, double h, double z)
 {
     double a = fabs(z);
     double mean, var;
@@ -676,25 +861,36 @@ normal_approx_sample(Rng& r, double h, double z)
         var = h / 24.0;
     }
     else {
-        double e = exp(-a);
-        double ope = 1.0 + e;
-        mean = 0.5 * h * ((1.0 - e) / ope) / a;
+        // tanh(a/2) = (1 - e)/(1 + e) and sech^2(a/2) = 4 e / (1 + e)^2 with e = e^{-a}; one
+        // reciprocal rinv = 1 / ((1 + e) a) serves the mean and the variance
+        const double e = exp(-a);
+        const double ope = 1.0 + e;
+        const double rinv = 1.0 / (ope * a);
+        mean = 0.5 * h * (1.0 - e) * rinv;
         if (a < 1.0) {
-            double a2 = a * a;
-            double S = 1.0 / 6.0 + a2 * (1.0 / 120.0 + a2 * (1.0 / 5040.0 + a2 * (1.0 / 362880.0 +
-                       a2 * (1.0 / 39916800.0 + a2 * (1.0 / 6227020800.0 + a2 * (1.0 / 1307674368000.0))))));
-            var = 0.25 * h * S * (4.0 * e / (ope * ope));
+            const double a2 = a * a;
+            // (sinh a - a) / a^3 = sum_k a^(2k) / (2k+3)!
+            const double S = 1.0 / 6.0 + a2 * (1.0 / 120.0 + a2 * (1.0 / 5040.0 + a2 * (1.0 / 362880.0 +
+                             a2 * (1.0 / 39916800.0 + a2 * (1.0 / 6227020800.0 + a2 * (1.0 / 1307674368000.0))))));
+            const double inv_ope = rinv * a;
+            var = h * S * e * inv_ope * inv_ope;
         }
         else {
-            var = 0.25 * h * 2.0 * (1.0 - e * e - 2.0 * a * e) / (ope * ope * a * a * a);
+            // (sinh a - a) sech^2(a/2) / (4 a^3) = (1 - e^2 - 2 a e) / (2 (1 + e)^2 a^3)
+            var = 0.5 * h * (1.0 - e * e - 2.0 * a * e) * rinv * rinv * (ope * rinv);
         }
     }
-    return mean + r.normal() * sqrt(var);
+    // mean + N sqrt(var) with the Box-Muller radius folded into one square root
+    const double u1 = r.uniform_oc();
+    const double u2 = r.uniform_co();
+    return mean + sqrt(-2.0 * var * log(u1)) * cospi(2.0 * u2);
 }
 
 // random_polyagamma_gamma_conv (src/pgm_random.c:79-97): 200 Marsaglia-Tsang gammas
+using GammaRng = RngFor<6>;
+
 __device__ inline double
-gamma_conv_sample(Rng& r, double h, double z)
+gamma_conv_sample(GammaRng& r, double h, double z)
 {
     double zz = 0.5 * fabs(z);
     if (!(zz > 0.0)) zz = 0.0;

@@ -92,11 +92,12 @@ profile_end(double* ms, uint64_t* launches, int cap)
 // ---------------------------------------------------------------------------------------
 // operand addressing: scalar / contiguous / broadcast-strided
 // ---------------------------------------------------------------------------------------
-__device__ __noinline__ void
+__device__ __forceinline__ void
 load_hz_strided(const FillArgs& a, uint64_t g, double& h, double& z)
 {
     int64_t oh = 0, oz = 0;
     uint64_t rem = g;
+#pragma unroll 1
     for (int d = a.bc.ndim - 1; d >= 0; --d) {
         uint64_t q = rem / (uint64_t)a.bc.shape[d];
         int64_t i = (int64_t)(rem - q * (uint64_t)a.bc.shape[d]);
@@ -143,10 +144,10 @@ constexpr int kBucketTile = kBucketThreads * kBucketItems;  // elements per bloc
 constexpr uint8_t kBucketNone = 255;
 
 // bucket ids (also the order of the per-method lists inside the chunk's index list)
-enum : int { kBDevroye = 0, kBAlternate = 1, kBSaddleFull = 2, kBSaddleLeft = 3, kBNormal = 4, kBGamma = 5,
-             kNumBuckets = 6 };
+enum : int { kBDevroye = 0, kBAlternate = 1, kBSaddleFull = 2, kBSaddleLeft = 3, kBSaddleFar = 4, kBAlternateLeft = 5,
+             kBNormal = 6, kBGamma = 7, kNumBuckets = 8 };
 
-// ctl layout (uint32): [0..5] bucket counts, [8..13] list bases, [16..21] work counters
+// ctl layout (uint32): [0..7] bucket counts, [8..15] list bases, [16..23] work counters
 constexpr int kCtlCount = 0, kCtlBase = 8, kCtlWork = 16, kCtlWords = 32;
 
 __host__ __device__ __forceinline__ int
@@ -154,100 +155,194 @@ bucket_of(int method, double h, double z, bool compat)
 {
     switch (method) {
         case kDevroye: return kBDevroye;
-        case kAlternate: return kBAlternate;
-        case kSaddle: return saddle_left_only(h, z, compat) ? kBSaddleLeft : kBSaddleFull;
+        case kAlternate: return alternate_left_only(z) ? kBAlternateLeft : kBAlternate;
+        case kSaddle: {
+            int sm = saddle_mode(h, z, compat);
+            return sm == kSaddleFull ? kBSaddleFull : sm == kSaddleLeft ? kBSaddleLeft : kBSaddleFar;
+        }
         case kNormal: return kBNormal;
         default: return kBGamma;
     }
 }
 
-// Thread t of warp w in block b owns elements  b*Tile + w*256 + k*32 + lane, k = 0..7.
+// Layout of the pre-pass: a block owns kTilesPerBlock consecutive tiles of kBucketTile elements;
+// thread t of a tile owns the 8 CONSECUTIVE elements tile*2048 + t*8 .. +7, so h and z are read
+// with 16-byte loads, the 8 bucket ids are stored as one 8-byte word, and every per-method list
+// comes out in ascending element order.  Per-bucket counts travel packed two to a 32-bit word
+// (16 bits each; a block never holds more than 8192 elements).
+constexpr int kTilesPerBlock = 4;
+constexpr int kPacked = (kNumBuckets + 1) / 2;
+
+__device__ __forceinline__ void
+packed_add(uint32_t (&pc)[kPacked], int bucket)
+{
+#pragma unroll
+    for (int w = 0; w < kPacked; ++w) {
+        pc[w] += (bucket == 2 * w) ? 1u : (bucket == 2 * w + 1) ? 0x10000u : 0u;
+    }
+}
+
+__device__ __forceinline__ uint32_t
+packed_get(const uint32_t (&pc)[kPacked], int q)
+{
+    return (q & 1) ? (pc[q >> 1] >> 16) : (pc[q >> 1] & 0xffffu);
+}
+
 // `method` is the requested sampler (kHybrid: src/pgm_random.c:105-121 decides per element).
+// VEC: h and z are contiguous, 16-byte aligned arrays (or scalars).
+template <bool VEC>
 __global__ void __launch_bounds__(kBucketThreads)
 classify_kernel(FillArgs a, uint32_t n, int method, uint8_t* __restrict__ meth, uint32_t* __restrict__ block_counts)
 {
-    __shared__ uint32_t s_cnt[kNumBuckets];
-    if (threadIdx.x < kNumBuckets) s_cnt[threadIdx.x] = 0;
+    __shared__ uint32_t s_cnt[kPacked];
+    if (threadIdx.x < kPacked) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t wbase = blockIdx.x * kBucketTile + warp * (32 * kBucketItems);
-    uint32_t cnt[kNumBuckets];
+    const bool compat = a.compat != 0;
+    uint32_t pc[kPacked];
 #pragma unroll
-    for (int q = 0; q < kNumBuckets; ++q) cnt[q] = 0;
-    for (int k = 0; k < kBucketItems; ++k) {
-        uint32_t e = wbase + k * 32 + lane;
-        uint8_t b = kBucketNone;
-        if (e < n) {
-            double h, z, bad;
-            load_hz(a, a.base + e, h, z);
+    for (int w = 0; w < kPacked; ++w) pc[w] = 0;
+    for (int tile = 0; tile < kTilesPerBlock; ++tile) {
+        const uint32_t e0 = (blockIdx.x * kTilesPerBlock + tile) * kBucketTile + threadIdx.x * kBucketItems;
+        if (e0 >= n) break;
+        const bool full = (e0 + kBucketItems <= n);
+        uint64_t word = 0;
+        auto classify_one = [&](int k, double h, double z) {
+            uint32_t b = kBucketNone;
+            double bad;
             if (invalid_h(h, bad)) {
-                a.out[a.base + e] = bad;
+                a.out[a.base + e0 + k] = bad;
             }
             else {
                 int m = (method == kHybrid) ? hybrid_select(h, z) : method;
-                b = (uint8_t)bucket_of(m, h, z, a.compat != 0);
+                b = (uint32_t)bucket_of(m, h, z, compat);
+                packed_add(pc, (int)b);
             }
-            meth[e] = b;
-        }
+            word |= (uint64_t)b << (8 * k);
+        };
+        if (VEC && full) {
+            double hv[kBucketItems], zv[kBucketItems];
+            const uint64_t g0 = a.base + e0;
+            if (a.h) {
+                const double2* p = reinterpret_cast<const double2*>(a.h + g0);
 #pragma unroll
-        for (int q = 0; q < kNumBuckets; ++q) {
-            cnt[q] += __popc(__ballot_sync(0xffffffffu, b == q));
+                for (int k = 0; k < kBucketItems / 2; ++k) {
+                    double2 v = __ldg(p + k);
+                    hv[2 * k] = v.x;
+                    hv[2 * k + 1] = v.y;
+                }
+            }
+            else {
+#pragma unroll
+                for (int k = 0; k < kBucketItems; ++k) hv[k] = a.h_scalar;
+            }
+            if (a.z) {
+                const double2* p = reinterpret_cast<const double2*>(a.z + g0);
+#pragma unroll
+                for (int k = 0; k < kBucketItems / 2; ++k) {
+                    double2 v = __ldg(p + k);
+                    zv[2 * k] = v.x;
+                    zv[2 * k + 1] = v.y;
+                }
+            }
+            else {
+#pragma unroll
+                for (int k = 0; k < kBucketItems; ++k) zv[k] = a.z_scalar;
+            }
+#pragma unroll
+            for (int k = 0; k < kBucketItems; ++k) classify_one(k, hv[k], zv[k]);
+        }
+        else {
+#pragma unroll 1
+            for (int k = 0; k < kBucketItems; ++k) {
+                if (e0 + k < n) {
+                    double h, z;
+                    load_hz(a, a.base + e0 + k, h, z);
+                    classify_one(k, h, z);
+                }
+                else {
+                    word |= (uint64_t)kBucketNone << (8 * k);
+                }
+            }
+        }
+        if (full) {
+            *reinterpret_cast<uint64_t*>(meth + e0) = word;
+        }
+        else {
+#pragma unroll
+            for (int k = 0; k < kBucketItems; ++k) {
+                if (e0 + k < n) meth[e0 + k] = (uint8_t)(word >> (8 * k));
+            }
         }
     }
-    if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < kNumBuckets; ++q) atomicAdd(&s_cnt[q], cnt[q]);
+    for (int w = 0; w < kPacked; ++w) {
+        // a warp holds at most 256 * kTilesPerBlock... per thread at most 32: sums stay < 2^16
+        for (int off = 16; off > 0; off >>= 1) pc[w] += __shfl_xor_sync(0xffffffffu, pc[w], off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int w = 0; w < kPacked; ++w) atomicAdd(&s_cnt[w], pc[w]);
     }
     __syncthreads();
-    if (threadIdx.x < kNumBuckets) block_counts[blockIdx.x * kNumBuckets + threadIdx.x] = s_cnt[threadIdx.x];
+    if (threadIdx.x < kNumBuckets) {
+        uint32_t v = s_cnt[threadIdx.x >> 1];
+        v = (threadIdx.x & 1) ? (v >> 16) : (v & 0xffffu);
+        block_counts[threadIdx.x * gridDim.x + blockIdx.x] = v;  // bucket-major
+    }
 }
 
-// One block: exclusive scan over blocks for each bucket; totals and list bases into ctl.
+// One block: exclusive scan over the pre-pass blocks for each bucket (block_counts is
+// bucket-major: [bucket][block]); totals and list bases into ctl.
 __global__ void __launch_bounds__(1024)
 scan_kernel(const uint32_t* __restrict__ block_counts, uint32_t nblocks, uint32_t* __restrict__ block_offsets,
             uint32_t* __restrict__ ctl)
 {
-    __shared__ uint32_t s_part[1024][kNumBuckets];
-    const uint32_t t = threadIdx.x;
+    __shared__ uint32_t s_warp[32][kNumBuckets];
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint32_t per = (nblocks + 1023) / 1024;
     const uint32_t lo = min(t * per, nblocks), hi = min(lo + per, nblocks);
-    uint32_t sum[kNumBuckets];
+    uint32_t sum[kNumBuckets], incl[kNumBuckets];
 #pragma unroll
-    for (int q = 0; q < kNumBuckets; ++q) sum[q] = 0;
-    for (uint32_t b = lo; b < hi; ++b) {
-#pragma unroll
-        for (int q = 0; q < kNumBuckets; ++q) sum[q] += block_counts[b * kNumBuckets + q];
+    for (int q = 0; q < kNumBuckets; ++q) {
+        uint32_t v = 0;
+        for (uint32_t b = lo; b < hi; ++b) v += block_counts[q * nblocks + b];
+        sum[q] = v;
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t up = __shfl_up_sync(0xffffffffu, v, off);
+            if (lane >= (uint32_t)off) v += up;
+        }
+        incl[q] = v;
+        if (lane == 31) s_warp[warp][q] = v;
     }
-#pragma unroll
-    for (int q = 0; q < kNumBuckets; ++q) s_part[t][q] = sum[q];
     __syncthreads();
-    // Hillis-Steele inclusive scan over the 1024 partials, all buckets at once
-    for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint32_t v[kNumBuckets];
-#pragma unroll
-        for (int q = 0; q < kNumBuckets; ++q) v[q] = (t >= off) ? s_part[t - off][q] : 0;
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < kNumBuckets; ++q) s_part[t][q] += v[q];
-        __syncthreads();
-    }
-    uint32_t run[kNumBuckets];
-#pragma unroll
-    for (int q = 0; q < kNumBuckets; ++q) run[q] = s_part[t][q] - sum[q];  // exclusive
-    for (uint32_t b = lo; b < hi; ++b) {
+    if (warp == 0) {
 #pragma unroll
         for (int q = 0; q < kNumBuckets; ++q) {
-            block_offsets[b * kNumBuckets + q] = run[q];
-            run[q] += block_counts[b * kNumBuckets + q];
+            uint32_t v = s_warp[lane][q];
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t up = __shfl_up_sync(0xffffffffu, v, off);
+                if (lane >= (uint32_t)off) v += up;
+            }
+            s_warp[lane][q] = v;  // inclusive over warps
         }
     }
-    if (t == 1023) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kNumBuckets; ++q) {
+        uint32_t run = incl[q] - sum[q] + (warp ? s_warp[warp - 1][q] : 0u);  // exclusive prefix of thread t
+        for (uint32_t b = lo; b < hi; ++b) {
+            block_offsets[q * nblocks + b] = run;
+            run += block_counts[q * nblocks + b];
+        }
+    }
+    if (t == 0) {
         uint32_t base = 0;
 #pragma unroll
         for (int q = 0; q < kNumBuckets; ++q) {
-            ctl[kCtlCount + q] = s_part[1023][q];
+            uint32_t total = s_warp[31][q];
+            ctl[kCtlCount + q] = total;
             ctl[kCtlBase + q] = base;
-            base += s_part[1023][q];
+            base += total;
         }
     }
 }
@@ -256,42 +351,63 @@ __global__ void __launch_bounds__(kBucketThreads)
 scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __restrict__ block_offsets,
                const uint32_t* __restrict__ ctl, uint32_t* __restrict__ list)
 {
-    __shared__ uint32_t s_warp[kBucketThreads / 32][kNumBuckets];
+    __shared__ uint32_t s_warp[kBucketThreads / 32][kPacked];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t wbase = blockIdx.x * kBucketTile + warp * (32 * kBucketItems);
-    uint8_t m[kBucketItems];
-    uint32_t cnt[kNumBuckets];
+    uint32_t run[kNumBuckets];  // next free list slot of each bucket for this block
 #pragma unroll
-    for (int q = 0; q < kNumBuckets; ++q) cnt[q] = 0;
+    for (int q = 0; q < kNumBuckets; ++q) run[q] = ctl[kCtlBase + q] + block_offsets[q * gridDim.x + blockIdx.x];
+    for (int tile = 0; tile < kTilesPerBlock; ++tile) {
+        const uint32_t t0 = (blockIdx.x * kTilesPerBlock + tile) * kBucketTile;
+        if (t0 >= n) break;  // block-uniform
+        const uint32_t e0 = t0 + threadIdx.x * kBucketItems;
+        uint64_t word = ~0ull;
+        if (e0 + kBucketItems <= n) {
+            word = *reinterpret_cast<const uint64_t*>(meth + e0);
+        }
+        else {
+            for (int k = 0; k < kBucketItems; ++k) {
+                if (e0 + k < n) word = (word & ~(0xffull << (8 * k))) | ((uint64_t)meth[e0 + k] << (8 * k));
+            }
+        }
+        uint32_t pc[kPacked];
 #pragma unroll
-    for (int k = 0; k < kBucketItems; ++k) {
-        uint32_t e = wbase + k * 32 + lane;
-        m[k] = (e < n) ? meth[e] : kBucketNone;
+        for (int w = 0; w < kPacked; ++w) pc[w] = 0;
 #pragma unroll
-        for (int q = 0; q < kNumBuckets; ++q) cnt[q] += __popc(__ballot_sync(0xffffffffu, m[k] == q));
-    }
-    if (lane == 0) {
+        for (int k = 0; k < kBucketItems; ++k) packed_add(pc, (int)((word >> (8 * k)) & 0xff));
+        uint32_t incl[kPacked];
 #pragma unroll
-        for (int q = 0; q < kNumBuckets; ++q) s_warp[warp][q] = cnt[q];
-    }
-    __syncthreads();
-    uint32_t off[kNumBuckets];
+        for (int w = 0; w < kPacked; ++w) {
+            uint32_t v = pc[w];
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t up = __shfl_up_sync(0xffffffffu, v, off);
+                if (lane >= (uint32_t)off) v += up;
+            }
+            incl[w] = v;
+            if (lane == 31) s_warp[warp][w] = v;
+        }
+        __syncthreads();
+        uint32_t before[kPacked], total[kPacked];
 #pragma unroll
-    for (int q = 0; q < kNumBuckets; ++q) {
-        uint32_t o = ctl[kCtlBase + q] + block_offsets[blockIdx.x * kNumBuckets + q];
-        for (uint32_t w = 0; w < warp; ++w) o += s_warp[w][q];
-        off[q] = o;
-    }
-    const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-    for (int k = 0; k < kBucketItems; ++k) {
-        uint32_t e = wbase + k * 32 + lane;
+        for (int w = 0; w < kPacked; ++w) {
+            uint32_t bsum = 0, tsum = 0;
+            for (uint32_t ww = 0; ww < kBucketThreads / 32; ++ww) {
+                uint32_t v = s_warp[ww][w];
+                tsum += v;
+                if (ww < warp) bsum += v;
+            }
+            before[w] = bsum + incl[w] - pc[w];  // elements of this tile ahead of this thread
+            total[w] = tsum;
+        }
 #pragma unroll
         for (int q = 0; q < kNumBuckets; ++q) {
-            uint32_t mask = __ballot_sync(0xffffffffu, m[k] == q);
-            if (m[k] == q) list[off[q] + __popc(mask & lt)] = e;
-            off[q] += __popc(mask);
+            uint32_t o = run[q] + packed_get(before, q);
+#pragma unroll
+            for (int k = 0; k < kBucketItems; ++k) {
+                if (((word >> (8 * k)) & 0xff) == (uint64_t)q) list[o++] = e0 + k;
+            }
+            run[q] += packed_get(total, q);
         }
+        __syncthreads();
     }
 }
 
@@ -386,7 +502,7 @@ sample_kernel(FillArgs a, Bucket b, uint32_t* __restrict__ counter)
 
     typename M::Par par;
     typename M::State st;
-    Rng rng;
+    typename M::Rng rng;
     uint64_t g = 0;
     bool active = false;
     uint32_t wnext = 0, wend = 0;  // warp-uniform reserved range of list positions
@@ -454,10 +570,31 @@ dense_kernel(FillArgs a, Bucket b)
             a.out[g] = bad;
             continue;
         }
-        Rng rng;
-        rng.init(a.key, a.first_index + g);
-        a.out[g] = (KIND == kNormal) ? normal_approx_sample(rng, h, z) : gamma_conv_sample(rng, h, z);
+        if (KIND == kNormal) {
+            RngInline rng;
+            rng.init(a.key, a.first_index + g);
+            a.out[g] = normal_approx_sample(rng, h, z);
+        }
+        else {
+            GammaRng rng;
+            rng.init(a.key, a.first_index + g);
+            a.out[g] = gamma_conv_sample(rng, h, z);
+        }
     }
+}
+
+// fills g_guess_uc / g_guess_ur (one thread per table entry)
+__global__ void
+init_guess_tables_kernel()
+{
+    using namespace saddle;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kGuessN) return;
+    double zz = (double)i / kGuessPerUnit;
+    double xl = zz > 0.0 ? tanh(zz) / zz : 1.0;
+    double f, fp;
+    g_guess_uc[i] = solve(2.75 * xl, table_guess(2.75 * xl), f, fp);
+    g_guess_ur[i] = solve(3.0 * xl, table_guess(3.0 * xl), f, fp);
 }
 
 __global__ void
@@ -485,7 +622,8 @@ check_h_kernel(const double* __restrict__ h, size_t n, int devroye, int* __restr
 // ---------------------------------------------------------------------------------------
 struct DeviceInfo {
     int sms = 0;
-    int blocks_per_sm[4] = {0, 0, 0, 0};  // devroye, alternate, saddle-full, saddle-left sampling kernels
+    // sampling kernels: devroye, alternate, saddle-full, saddle-left, saddle-far, alternate-left
+    int blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};
 };
 
 static DeviceInfo
@@ -501,9 +639,15 @@ device_info()
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[1], sample_kernel<Alternate>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[2], sample_kernel<SaddleFull>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[3], sample_kernel<SaddleLeft>, kPersistThreads, 0);
-        for (int i = 0; i < 4; ++i) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[4], sample_kernel<SaddleFar>, kPersistThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[5], sample_kernel<AlternateLeft>, kPersistThreads, 0);
+        for (int i = 0; i < 6; ++i) {
             if (d.blocks_per_sm[i] < 1) d.blocks_per_sm[i] = 1;
         }
+        // starting-point tables of the saddle setup (per device, filled by the solver itself)
+        init_guess_tables_kernel<<<(saddle::kGuessN + 127) / 128, 128>>>();
+        cudaDeviceSynchronize();
+        count_launch(1);
         // stream-ordered scratch: keep freed blocks cached in the pool instead of returning
         // them to the OS at every synchronisation
         cudaMemPool_t pool;
@@ -523,14 +667,17 @@ grid_for(uint64_t full, uint64_t count_hint, uint32_t threads)
     return (uint32_t)(need < full ? need : full);
 }
 
-// setup + persistent sampling of one bucket with method M (which: 0..3, kind: profiling id)
+// setup + persistent sampling of one bucket with method M (which: 0 devroye, 1 alternate,
+// 2 saddle-full, 3 saddle-left, 4 saddle-far, 5 alternate-left; profiling kinds are
+// kKindDevroye / kKindSetup + which)
 template <class M>
 static void
-launch_method(const DeviceInfo& d, int which, int kind, const FillArgs& a, const Bucket& b, uint64_t count_hint,
+launch_method(const DeviceInfo& d, int which, const FillArgs& a, const Bucket& b, uint64_t count_hint,
               uint32_t* counter, cudaStream_t s)
 {
+    const int kind = kKindDevroye + which;
     {
-        ScopedKernelTimer timer(kKindSetup, s);
+        ScopedKernelTimer timer(kKindSetup + which, s);
         uint64_t nrec = b.uniform ? 1 : count_hint;
         setup_kernel<M><<<grid_for((uint64_t)d.sms * 8, nrec, 256), 256, 0, s>>>(a, b);
     }
@@ -597,10 +744,12 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
             a.base = base0 + off;
             Bucket b{nullptr, nullptr, bk, cn, params, 1};
             switch (bk) {
-                case kBDevroye: launch_method<Devroye>(d, 0, kKindDevroye, a, b, cn, counters + c, s); break;
-                case kBAlternate: launch_method<Alternate>(d, 1, kKindAlternate, a, b, cn, counters + c, s); break;
-                case kBSaddleFull: launch_method<SaddleFull>(d, 2, kKindSaddle, a, b, cn, counters + c, s); break;
-                case kBSaddleLeft: launch_method<SaddleLeft>(d, 3, kKindSaddleLeft, a, b, cn, counters + c, s); break;
+                case kBDevroye: launch_method<Devroye>(d, 0, a, b, cn, counters + c, s); break;
+                case kBAlternate: launch_method<Alternate>(d, 1, a, b, cn, counters + c, s); break;
+                case kBSaddleFull: launch_method<SaddleFull>(d, 2, a, b, cn, counters + c, s); break;
+                case kBSaddleLeft: launch_method<SaddleLeft>(d, 3, a, b, cn, counters + c, s); break;
+                case kBSaddleFar: launch_method<SaddleFar>(d, 4, a, b, cn, counters + c, s); break;
+                case kBAlternateLeft: launch_method<AlternateLeft>(d, 5, a, b, cn, counters + c, s); break;
                 case kBNormal: launch_dense<kNormal>(d, a, b, cn, s); break;
                 default: launch_dense<kGamma>(d, a, b, cn, s); break;
             }
@@ -609,11 +758,11 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         return (int)cudaGetLastError();
     }
 
-    // per-element parameters (fill2).  hybrid and saddle need the bucketing pre-pass (several
-    // kernels per chunk); devroye / alternate / gamma run on the identity range.
-    const bool bucketed = (m == kHybrid || m == kSaddle);
+    // per-element parameters (fill2).  hybrid, saddle and alternate need the bucketing pre-pass
+    // (they split into specialised kernels); devroye and gamma run on the identity range.
+    const bool bucketed = (m == kHybrid || m == kSaddle || m == kAlternate);
     const uint64_t cmax = n < kChunk ? n : kChunk;
-    const uint32_t nblocks_max = (uint32_t)((cmax + kBucketTile - 1) / kBucketTile);
+    const uint32_t nblocks_max = (uint32_t)((cmax + kBucketTile * kTilesPerBlock - 1) / (kBucketTile * kTilesPerBlock));
     const size_t list_bytes = bucketed ? align256(cmax * sizeof(uint32_t)) : 0;
     const size_t meth_bytes = bucketed ? align256(cmax) : 0;
     const size_t hist_bytes = bucketed ? align256((size_t)nblocks_max * kNumBuckets * sizeof(uint32_t)) : 0;
@@ -631,6 +780,9 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     uint32_t* ctl = (uint32_t*)(ws + list_bytes + meth_bytes + 2 * hist_bytes);
     double* params = (double*)(ws + list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes);
 
+    // 16-byte loads in the pre-pass need contiguous, aligned operands (a scalar operand is fine)
+    const bool vec = a.bc.ndim == 0 && (a.h == nullptr || (a.h_stride == 1 && ((uintptr_t)(a.h + a.base) & 15) == 0)) &&
+                     (a.z == nullptr || (a.z_stride == 1 && ((uintptr_t)(a.z + a.base) & 15) == 0));
     const uint64_t base0 = a.base;
     for (uint64_t off = 0; off < n; off += kChunk) {
         const uint32_t cn = (uint32_t)((n - off) < kChunk ? (n - off) : kChunk);
@@ -639,16 +791,20 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         if (!bucketed) {
             Bucket b{nullptr, nullptr, 0, cn, params, 0};
             switch (m) {
-                case kDevroye: launch_method<Devroye>(d, 0, kKindDevroye, a, b, cn, ctl + kCtlWork, s); break;
-                case kAlternate: launch_method<Alternate>(d, 1, kKindAlternate, a, b, cn, ctl + kCtlWork, s); break;
+                case kDevroye: launch_method<Devroye>(d, 0, a, b, cn, ctl + kCtlWork, s); break;
                 default: launch_dense<kGamma>(d, a, b, cn, s); break;
             }
             continue;
         }
-        const uint32_t nblocks = (cn + kBucketTile - 1) / kBucketTile;
+        const uint32_t nblocks = (cn + kBucketTile * kTilesPerBlock - 1) / (kBucketTile * kTilesPerBlock);
         {
             ScopedKernelTimer timer(kKindClassify, s);
-            classify_kernel<<<nblocks, kBucketThreads, 0, s>>>(a, cn, m, meth, block_counts);
+            if (vec) {
+                classify_kernel<true><<<nblocks, kBucketThreads, 0, s>>>(a, cn, m, meth, block_counts);
+            }
+            else {
+                classify_kernel<false><<<nblocks, kBucketThreads, 0, s>>>(a, cn, m, meth, block_counts);
+            }
         }
         {
             ScopedKernelTimer timer(kKindScan, s);
@@ -662,11 +818,17 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         // counts and list bases stay on the device: the method kernels read them there, so the
         // host never waits for the histogram (empty buckets cost one near-empty launch)
         auto bucket = [&](int q) { return Bucket{list, ctl, q, 0, params, 0}; };
-        launch_method<SaddleFull>(d, 2, kKindSaddle, a, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s);
-        launch_method<SaddleLeft>(d, 3, kKindSaddleLeft, a, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s);
+        if (m != kAlternate) {
+            launch_method<SaddleFull>(d, 2, a, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s);
+            launch_method<SaddleLeft>(d, 3, a, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s);
+            launch_method<SaddleFar>(d, 4, a, bucket(kBSaddleFar), cn, ctl + kCtlWork + kBSaddleFar, s);
+        }
+        if (m != kSaddle) {
+            launch_method<Alternate>(d, 1, a, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s);
+            launch_method<AlternateLeft>(d, 5, a, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft, s);
+        }
         if (m == kHybrid) {
-            launch_method<Alternate>(d, 1, kKindAlternate, a, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s);
-            launch_method<Devroye>(d, 0, kKindDevroye, a, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s);
+            launch_method<Devroye>(d, 0, a, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s);
             launch_dense<kNormal>(d, a, bucket(kBNormal), cn, s);
         }
     }
