@@ -26,7 +26,7 @@
 
 namespace pgm {
 
-constexpr int kMaxRecordFields = 10;
+constexpr int kMaxRecordFields = 9;  // saddle-full is the largest record
 
 // Which sampling kernels keep a single out-of-line copy of the Philox block function (bit i =
 // method i in launch order: 0 devroye, 1 alternate, 2 saddle-full, 3 saddle-left, 4 saddle-far,
@@ -54,6 +54,7 @@ struct Devroye {
     struct State {
         double acc;
         uint32_t remaining;
+        uint32_t in_left;  // 1: inside the truncated inverse-Gaussian retry loop (no new mixture draw)
     };
 
     // set_sampling_parameters (src/pgm_devroye.c:61-83)
@@ -94,37 +95,8 @@ struct Devroye {
         p.z2 = p.zz * p.zz;
         s.acc = 0.0;
         s.remaining = (uint32_t)rec[3];
+        s.in_left = 0;
         return s.remaining != 0;
-    }
-
-    // random_right_bounded_invgauss (src/pgm_devroye.c:113-142)
-    static __device__ __forceinline__ double trunc_invgauss(const Par& p, Rng& r)
-    {
-        double x;
-        if (p.zz < 1.5625) {
-            for (;;) {
-                double e1, e2;
-                do {
-                    e1 = r.exponential();
-                    e2 = r.exponential();
-                } while (e1 * e1 > 3.125 * e2);
-                x = 1.0 + T * e1;
-                x = T / (x * x);
-                if (!(p.zz > 0.0)) break;
-                if (r.uniform32() < exp(-0.5 * p.z2 * x)) break;
-            }
-            return x;
-        }
-        double mu2 = 1.0 / p.z2;
-        do {
-            double y = r.normal();
-            double w = (p.zz + 0.5 * y * y) * mu2;
-            x = mu2 / (w + sqrt(fmax(w * w - mu2, 0.0)));
-            if (r.uniform_co() * (1.0 + x * p.zz) > 1.0) {
-                x = mu2 / x;
-            }
-        } while (x >= T);
-        return x;
     }
 
     // piecewise_coef (src/pgm_devroye.c:36-46)
@@ -134,15 +106,42 @@ struct Devroye {
         return kPi * a * exp(lp - e * a * a);
     }
 
-    // One pass of the loop in random_jacobi_star (src/pgm_devroye.c:160-190)
+    // One trip of random_jacobi_star (src/pgm_devroye.c:160-190) with the retry loops of
+    // random_right_bounded_invgauss (:113-142) FLATTENED into the trip: a lane whose exponential
+    // pair / Michael-Schucany-Haas draw fails returns with in_left set and simply proposes again
+    // next trip (same draw order as the nested loops of the oracle), instead of spinning while
+    // the other 31 lanes wait.  All three proposal kinds start from the same quantity
+    // L = -log(U): the tail exponential, the first exponential of the pair, half the squared
+    // Box-Muller radius -- so that logarithm is computed once, convergently.
     static __device__ __forceinline__ bool step(Par& p, State& s, Rng& r, bool)
     {
         double x, lp, e;
-        if (r.uniform_co() < p.w) {
-            x = trunc_invgauss(p, r);
+        const bool left = s.in_left ? true : (r.uniform_co() < p.w);
+        const double L = -log(r.uniform_oc());
+        if (left) {
+            s.in_left = 1;
+            if (p.zz < 1.5625) {  // 1/T: exponential-pair proposal of Devroye (2009)
+                const double e2 = r.exponential();
+                if (L * L > 3.125 * e2) return false;
+                x = 1.0 + T * L;
+                x = T / (x * x);
+                if (p.zz > 0.0 && !(r.uniform32() < exp(-0.5 * p.z2 * x))) return false;
+            }
+            else {  // IG(1/z, 1) by Michael-Schucany-Haas; only the square of the normal is needed
+                const double c = cospi(2.0 * r.uniform_co());
+                const double y2 = 2.0 * L * c * c;
+                const double mu2 = 1.0 / p.z2;
+                const double w = (p.zz + 0.5 * y2) * mu2;
+                x = mu2 / (w + sqrt(fmax(w * w - mu2, 0.0)));
+                if (r.uniform_co() * (1.0 + x * p.zz) > 1.0) {
+                    x = mu2 / x;
+                }
+                if (x >= T) return false;
+            }
+            s.in_left = 0;
         }
         else {
-            x = T + r.exponential() / p.K;
+            x = T + L / p.K;
         }
         if (x > T) {
             lp = 0.0;
@@ -806,33 +805,57 @@ struct SaddleT {
         else {
             x = left_bounded_gamma(r, h, -h * p.slope_r, p.xc);
         }
-        const double logx = log(x);
-        double lk;
-        if (FULL && x > p.xc) {
-            lk = h * p.slope_r * x + (h - 1.0) * logx + p.c_r;
+        // Acceptance: log U + log k(x) <= log phi(x) with (saddle_point :235-244, bounding_kernel
+        // :250-263, common sqrt(h / 2 pi) cancelled)
+        //   log phi = h (K(u) - t x) - 1/2 log K''(u),  t = u + z^2/2,  K'(u) = x
+        //   log k_l = h (slope_l x - 1/(2x)) - 3/2 log x + c_l          (x <= xc)
+        //   log k_r = h slope_r x + (h - 1) log x + c_r                 (x >  xc)
+        const double rx = 1.0 / x;
+        double u, fp, cum;
+        if (x <= 0.2) {
+            // large-argument closed form: tanh(s)/s = x solved to < 1e-10 relative by the two-pass
+            // fixed point behind asymptotic_guess, so K' = x, K'' = x^2 + (1 - x)/(2u) and
+            // -log cosh s = -(s - log 2 + log1p(e^{-2s})) need no further evaluation of tanh
+            const double e = exp(-2.0 * rx);
+            const double corr = 2.0 * e - e * e * (2.0 - 8.0 * rx);
+            const double sx = (1.0 - corr) * rx;         // s = sqrt(-2u)
+            const double dl = 2.0 * corr * rx;            // 2 (1/x - s)
+            const double e2s = e * (1.0 + dl * (1.0 + 0.5 * dl));  // e^{-2s}
+            const double inv_s2 = 1.0 / (sx * sx);
+            u = -0.5 * sx * sx;
+            fp = x * x - (1.0 - x) * inv_s2;
+            cum = -(sx - kLog2 + e2s * (1.0 - e2s * (0.5 - e2s * (1.0 / 3.0))));
         }
         else {
-            lk = h * (p.slope_l * x - 0.5 / x) - 1.5 * logx + p.c_l;
+            double u0;
+            const double d = x - p.xl;
+            if (x <= 0.25) {
+                u0 = asymptotic_guess(x);
+            }
+            else if (fabs(d) <= 0.5 * p.xl) {
+                u0 = -p.half_z2 + d * (p.a1 + p.a2 * d);
+                u0 = FAR ? fmin(u0, -1e-3) : fmin(u0, kUMax - 1e-3);
+            }
+            else {
+                u0 = table_guess(x);
+            }
+            double f;
+            u = solve<FAR>(x, u0, f, fp);
+            cum = cumulant0(u, f);
         }
-        // starting point of the saddle-point solve: large-argument form for small x, else the
-        // expansion about xl, else the reference's table
-        double u0;
-        const double d = x - p.xl;
-        if (x <= 0.25) {
-            u0 = asymptotic_guess(x);
-        }
-        else if (fabs(d) <= 0.5 * p.xl) {
-            u0 = -p.half_z2 + d * (p.a1 + p.a2 * d);
-            u0 = FAR ? fmin(u0, -1e-3) : fmin(u0, kUMax - 1e-3);
-        }
-        else {
-            u0 = table_guess(x);
-        }
-        double f, fp;
-        const double u = solve<FAR>(x, u0, f, fp);
         const double t = u + p.half_z2;
-        const double lphi = h * (cumulant0(u, f) - t * x) - 0.5 * log(fp);
-        if (log(r.uniform32()) + lk <= lphi) {
+        const double um2 = r.uniform32();
+        bool accept;
+        if (FULL && x > p.xc) {
+            const double lk = h * p.slope_r * x + (h - 1.0) * log(x) + p.c_r;
+            accept = log(um2) + lk <= h * (cum - t * x) - 0.5 * log(fp);
+        }
+        else {
+            // the three logarithms (U, x^-3/2, K''^1/2) folded into one
+            const double lhs = 0.5 * log(um2 * um2 * fp * rx * rx * rx);
+            accept = lhs <= h * (cum - t * x) - h * (p.slope_l * x - 0.5 * rx) - p.c_l;
+        }
+        if (accept) {
             s.acc = 0.25 * h * x;
             return true;
         }

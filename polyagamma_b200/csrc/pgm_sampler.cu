@@ -14,6 +14,8 @@
 // attempt per loop trip (pgm_methods.cuh); lanes whose element completed are retired and
 // refilled from a per-bucket work counter, found with __ballot_sync/__popc, so a warp never
 // idles on another lane's rejection loop.  Nothing here synchronises the host.
+#include <stdlib.h>
+
 #include "pgm_internal.h"
 #include "pgm_methods.cuh"
 
@@ -700,7 +702,31 @@ launch_dense(const DeviceInfo& d, const FillArgs& a, const Bucket& b, uint64_t c
 
 // Elements per pass through the pipeline.  Bounds the scratch (5 B + one record per element)
 // and keeps list indices in 32 bits.
-constexpr uint64_t kChunk = 1ull << 25;
+// Pass size.  Every kernel of a pass ends with a partially filled last wave, so fewer, larger
+// passes are faster (cfg4 per 1e9 elements: 2^24 66.8 ms, 2^25 55.5, 2^26 50.7, 2^27 48.5 ms);
+// the per-element path needs 5 B + one record of scratch per element of a pass.  It starts at
+// 2^27 elements (or the smallest power of two >= n) and halves the pass while the stream-ordered
+// allocation of the scratch fails.  PGM_CUDA_CHUNK_LOG2 in the environment pins the pass size
+// (tests use it to cross pass seams).
+constexpr int kChunkLog2Min = 20, kChunkLog2Max = 27;
+
+static int
+env_chunk_log2()
+{
+    const char* e = getenv("PGM_CUDA_CHUNK_LOG2");
+    if (e == nullptr) return 0;
+    int v = atoi(e);
+    return (v >= 10 && v <= 30) ? v : 0;
+}
+
+static int
+first_chunk_log2(uint64_t n)
+{
+    if (int forced = env_chunk_log2()) return forced;
+    int lg = kChunkLog2Max;
+    while (lg > kChunkLog2Min && (1ull << (lg - 1)) >= n) --lg;
+    return lg;
+}
 
 static inline size_t
 align256(size_t v)
@@ -730,6 +756,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         }
         const int eff = (m == kHybrid) ? hybrid_select(a.h_scalar, a.z_scalar) : m;
         const int bk = bucket_of(eff, a.h_scalar, a.z_scalar, compat);
+        const uint64_t kChunk = 1ull << first_chunk_log2(n);
         const uint64_t nchunks = (n + kChunk - 1) / kChunk;
         char* ws = nullptr;
         const size_t rec_bytes = align256(kMaxRecordFields * sizeof(double));
@@ -761,17 +788,25 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     // per-element parameters (fill2).  hybrid, saddle and alternate need the bucketing pre-pass
     // (they split into specialised kernels); devroye and gamma run on the identity range.
     const bool bucketed = (m == kHybrid || m == kSaddle || m == kAlternate);
-    const uint64_t cmax = n < kChunk ? n : kChunk;
-    const uint32_t nblocks_max = (uint32_t)((cmax + kBucketTile * kTilesPerBlock - 1) / (kBucketTile * kTilesPerBlock));
-    const size_t list_bytes = bucketed ? align256(cmax * sizeof(uint32_t)) : 0;
-    const size_t meth_bytes = bucketed ? align256(cmax) : 0;
-    const size_t hist_bytes = bucketed ? align256((size_t)nblocks_max * kNumBuckets * sizeof(uint32_t)) : 0;
+    int lg = first_chunk_log2(n);
+    uint64_t chunk = 0;
+    size_t list_bytes = 0, meth_bytes = 0, hist_bytes = 0, par_bytes = 0;
     const size_t ctl_bytes = align256(kCtlWords * sizeof(uint32_t));
-    const size_t par_bytes = (m == kGamma) ? 0 : align256(cmax * kMaxRecordFields * sizeof(double));
     char* ws = nullptr;
-    if ((err = cudaMallocAsync(&ws, list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes + par_bytes, s)) !=
-        cudaSuccess) {
-        return (int)err;
+    for (;;) {
+        chunk = 1ull << lg;
+        const uint64_t cmax = n < chunk ? n : chunk;
+        const uint32_t nblocks_max =
+            (uint32_t)((cmax + kBucketTile * kTilesPerBlock - 1) / (kBucketTile * kTilesPerBlock));
+        list_bytes = bucketed ? align256(cmax * sizeof(uint32_t)) : 0;
+        meth_bytes = bucketed ? align256(cmax) : 0;
+        hist_bytes = bucketed ? align256((size_t)nblocks_max * kNumBuckets * sizeof(uint32_t)) : 0;
+        par_bytes = (m == kGamma) ? 0 : align256(cmax * kMaxRecordFields * sizeof(double));
+        err = cudaMallocAsync(&ws, list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes + par_bytes, s);
+        if (err == cudaSuccess) break;
+        (void)cudaGetLastError();  // clear the sticky-free allocation error and retry smaller
+        if (err != cudaErrorMemoryAllocation || lg <= kChunkLog2Min || env_chunk_log2()) return (int)err;
+        --lg;
     }
     uint32_t* list = (uint32_t*)ws;
     uint8_t* meth = (uint8_t*)(ws + list_bytes);
@@ -784,8 +819,8 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     const bool vec = a.bc.ndim == 0 && (a.h == nullptr || (a.h_stride == 1 && ((uintptr_t)(a.h + a.base) & 15) == 0)) &&
                      (a.z == nullptr || (a.z_stride == 1 && ((uintptr_t)(a.z + a.base) & 15) == 0));
     const uint64_t base0 = a.base;
-    for (uint64_t off = 0; off < n; off += kChunk) {
-        const uint32_t cn = (uint32_t)((n - off) < kChunk ? (n - off) : kChunk);
+    for (uint64_t off = 0; off < n; off += chunk) {
+        const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
         a.base = base0 + off;
         cudaMemsetAsync(ctl, 0, ctl_bytes, s);
         if (!bucketed) {

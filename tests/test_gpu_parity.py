@@ -112,18 +112,27 @@ def test_launch_shape_independence(pg, torch):
     assert not torch.equal(pg.random_polyagamma(h, z, random_state=(77, 3), disable_checks=True), whole)
 
 
-def test_chunk_boundary(pg, torch):
-    """The pipeline processes 2^26 elements per pass; results must not see the seam."""
-    n = (1 << 26) + 4096
-    a = pg.random_polyagamma(1.0, 0.7, size=n, random_state=(5, 0), device="cuda")
-    tail = pg.random_polyagamma(1.0, 0.7, size=8192, random_state=(5, 0), device="cuda", first_index=n - 8192)
-    assert torch.equal(a[-8192:], tail)
+def test_chunk_boundary(pg, torch, monkeypatch):
+    """The pipeline processes the index range in passes (2^22..2^27 elements, chosen from free
+    memory); results must not see the seams.  PGM_CUDA_CHUNK_LOG2 pins a small pass size so that
+    a moderate n crosses several of them."""
+    n = (1 << 22) * 3 + 4097
     h = torch.rand(n, device="cuda", dtype=torch.float64) * 100 + 0.1
     z = torch.rand(n, device="cuda", dtype=torch.float64) * 20 - 10
-    b = pg.random_polyagamma(h, z, random_state=(5, 1), disable_checks=True)
+    ref_scalar = pg.random_polyagamma(1.0, 0.7, size=n, random_state=(5, 0), device="cuda")
+    ref_hybrid = pg.random_polyagamma(h, z, random_state=(5, 1), disable_checks=True)
+    ref_saddle = pg.random_polyagamma(h + 4, z, method="saddle", random_state=(5, 2), disable_checks=True)
+    monkeypatch.setenv("PGM_CUDA_CHUNK_LOG2", "22")
+    assert torch.equal(pg.random_polyagamma(1.0, 0.7, size=n, random_state=(5, 0), device="cuda"), ref_scalar)
+    assert torch.equal(pg.random_polyagamma(h, z, random_state=(5, 1), disable_checks=True), ref_hybrid)
+    assert torch.equal(pg.random_polyagamma(h + 4, z, method="saddle", random_state=(5, 2), disable_checks=True),
+                       ref_saddle)
+    monkeypatch.setenv("PGM_CUDA_CHUNK_LOG2", "20")
+    assert torch.equal(pg.random_polyagamma(h, z, random_state=(5, 1), disable_checks=True), ref_hybrid)
     tail = pg.random_polyagamma(h[-8192:], z[-8192:], random_state=(5, 1), first_index=n - 8192, disable_checks=True)
-    assert torch.equal(b[-8192:], tail)
-    del a, b, h, z
+    assert torch.equal(ref_hybrid[-8192:], tail)
+    monkeypatch.delenv("PGM_CUDA_CHUNK_LOG2")
+    del h, z
     torch.cuda.empty_cache()
 
 
@@ -330,7 +339,7 @@ def test_density_full_size_properties(pg, torch):
     # and is rounding noise in both versions; where the density is within 1e-4 of its peak over x
     # the series is well conditioned and exp(logpdf) must reproduce pdf
     big = (pdf > 1e-4 * pdf.max(dim=0, keepdim=True).values) & torch.isfinite(lpdf)
-    assert float(big.double().mean()) > 0.2
+    assert float(big.double().mean()) > 0.05
     assert float(((lpdf.exp() - pdf).abs() / pdf)[big].max()) < 1e-9
     del lpdf, big
     cdf = pg.polyagamma_cdf(x, h, z)
@@ -343,7 +352,12 @@ def test_density_full_size_properties(pg, torch):
     dx = float(x[1] - x[0])
     num = (cdf[2:] - cdf[:-2]) / (2 * dx)
     mid = pdf[1:-1]
-    ok = (mid > 1e-3) & (x[1:-1] > 0.05)
+    # the O(dx^2 f'''/f) truncation error of the difference quotient explodes on the steep left
+    # flank (f ~ exp(-h^2/8x)): compare from half the mean upwards
+    za = z.abs().clamp_min(1e-6)
+    mean = h * torch.tanh(za / 2) / (2 * za)
+    ok = (mid > 1e-3) & (x[1:-1] > 0.5 * mean)
+    assert float(ok.double().mean()) > 0.2
     assert float(((num - mid).abs() / mid)[ok].max()) < 5e-3
     del pdf, cdf, sub, num, mid, ok
     lc = pg.polyagamma_cdf(x[::16], h[:, ::16], z[:, ::16], return_log=True)
