@@ -305,6 +305,10 @@ def main():
         "hbm": {"achieved_gbs": n * args.steps * BYTES_PER_ELEMENT / (elapsed_ms * 1e-3) / 1e9,
                 "peak_gbs": hbm_peak, "frac": n * args.steps * BYTES_PER_ELEMENT / (elapsed_ms * 1e-3) / 1e9 / hbm_peak,
                 "bytes_per_unit": BYTES_PER_ELEMENT, "peak_source": peaks_src},
+        "per_kernel": {k: {"ms_per_step": kernels[k][0] / args.steps, "units_per_step": units[k],
+                           "tflops": units[k] * args.steps * FLOPS_PER_ELEMENT[k] / (kernels[k][0] * 1e-3) / 1e12,
+                           "frac": units[k] * args.steps * FLOPS_PER_ELEMENT[k] / (kernels[k][0] * 1e-3) / 1e12 / fp64_peak}
+                       for k in units if kernels[k][1] and kernels[k][0] > 0 and units[k] > 0},
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kernels.items() if v[1]},
         "kernel_launches": {k: v[1] for k, v in kernels.items() if v[1]},
     }

@@ -61,7 +61,7 @@ pg_logpdf(double x, double h, double z)
     double a = (fabs(z) > 0.0 ? h * log(cosh(0.5 * z)) - 0.5 * z * z * x : 0.0) + (h - 1.0) * kLog2 - kLs2Pi -
                1.5 * log(x);
     double first = -0.125 * h * h * inv_x;  // the reference's lgamma(h) cancels against `a`
-    double term = 1.0, sum = 1.0, sign = -1.0;
+    double term = 1.0, sum = 1.0, sign = -1.0, prev_term = 1.0;
     double q = exp(-inv_x);
     double g = exp(-0.5 * (h + 1.0) * inv_x);
     for (int n = 1; n < kMaxSeriesTerms; ++n, sign = -sign) {
@@ -69,7 +69,11 @@ pg_logpdf(double x, double h, double z)
         term *= ((dn - 1.0 + h) * (2.0 * dn + h)) / (dn * (2.0 * dn - 2.0 + h)) * g;
         g *= q;
         sum += sign * term;
-        if (term == 0.0) break;  // every later term is zero as well
+        // The reference adds all 199 terms.  Past their peak the terms decrease monotonically
+        // (log-concave in n), so once one is below 1e-30 |sum| neither it nor any later term can
+        // change the double-precision sum: stopping here is bit-identical to going on.
+        if (term < prev_term && term <= 1e-30 * fabs(sum)) break;
+        prev_term = term;
     }
     return a + (log(h) + first + log(sum));
 }
@@ -128,6 +132,31 @@ piece_logcdf(bool ig, double a, double s2x, double x, double z)
     return ig ? invgauss_logcdf(a, s2x, x, z) : invgamma_logcdf(a, s2x);
 }
 
+// The same piece in linear space, for the (overwhelmingly common) arguments where the reference
+// takes none of its tail approximations:
+//   z > 0:  F = Phi(A) + e^{z a} Phi(-B),  A = z sqrt(x) - a / (2 sqrt(x)),  B = z sqrt(x) + a / (2 sqrt(x))
+//             = 1/2 erfc(-A / sqrt 2) + 1/2 erfcx(B / sqrt 2) e^{-A^2 / 2}        (z a - B^2/2 = -A^2/2)
+//   z = 0:  F = erfc(a / (2 sqrt(2x)))
+// One erfc, one erfcx and one exp, no branch, instead of two (erf|erfc) + two log + log1p + exp
+// behind four data-dependent branches.  Returns false where the reference switches to the Bryc
+// (A < -37.5 or B > 37.5, src/pgm_density.c:184-194) or A&S 7.1.28 (:154-163) forms: the caller
+// then takes the log-space path, which reproduces them.
+__device__ __forceinline__ bool
+piece_cdf_fast(bool ig, double a, double sx, double half_rsx, double zsx, double& F)
+{
+    if (ig) {
+        const double t = a * half_rsx;  // a / (2 sqrt(x))
+        const double A = zsx - t, B = zsx + t;
+        if (A < -37.5 || B > 37.5) return false;
+        F = 0.5 * erfc(-0.7071067811865475 * A) + 0.5 * erfcx(0.7071067811865475 * B) * exp(-0.5 * A * A);
+        return true;
+    }
+    const double t = 0.5 * a / sx;  // sx = sqrt(2x)
+    if (t > 26.55) return false;
+    F = erfc(t);
+    return true;
+}
+
 // pgm_polyagamma_cdf (src/pgm_density.c:236-280)
 __device__ __forceinline__ double
 pg_cdf(double x, double h, double z)
@@ -146,14 +175,29 @@ pg_cdf(double x, double h, double z)
         c = h * kLog2;
         s2x = sqrt(2.0 * x);
     }
-    double sum = exp(c + piece_logcdf(ig, h, s2x, x, z));
+    const double half_rsx = 0.5 / s2x, zsx = z * s2x, ez = exp(-z);
+    // ck_n = e^c Gamma(n+h) / (Gamma(h) n!) e^{-n z}, by recurrence; for h > 300 it can overflow and
+    // the series (hopelessly ill-conditioned there anyway) stays in log space like the reference
+    const bool linear = h <= 300.0;
+    double ck = exp(c), lc = 0.0;
+    double F;
+    double sum = (linear && piece_cdf_fast(ig, h, s2x, half_rsx, zsx, F)) ? ck * F
+                                                                           : exp(c + piece_logcdf(ig, h, s2x, x, z));
     double sign = -1.0;
-    double lc = 0.0;  // log(Gamma(n+h) / (Gamma(h) n!))
     for (int n = 1; n < kMaxSeriesTerms; ++n, sign = -sign) {
-        double dn = (double)n;
-        lc += log((dn - 1.0 + h) / dn);
-        double term = exp(c + lc + piece_logcdf(ig, 2.0 * dn + h, s2x, x, z) - z * dn);
-        double prev = sum;
+        const double dn = (double)n;
+        const double a = 2.0 * dn + h;
+        double term;
+        if (linear) {
+            ck *= (dn - 1.0 + h) / dn * ez;
+            term = piece_cdf_fast(ig, a, s2x, half_rsx, zsx, F) ? ck * F
+                                                                 : exp(log(ck) + piece_logcdf(ig, a, s2x, x, z));
+        }
+        else {
+            lc += log((dn - 1.0 + h) / dn);
+            term = exp(c + lc + piece_logcdf(ig, a, s2x, x, z) - z * dn);
+        }
+        const double prev = sum;
         sum += sign * term;
         if (stagnated(sum, prev)) break;
     }
@@ -178,13 +222,33 @@ pg_logcdf(double x, double h, double z)
         c = h * kLog2;
         s2x = sqrt(2.0 * x);
     }
-    double first = piece_logcdf(ig, h, s2x, x, z);  // the reference's lgamma(h) cancels
-    double sum = 1.0, sign = -1.0, lc = 0.0;
+    const double half_rsx = 0.5 / s2x, zsx = z * s2x, ez = exp(-z);
+    const double first = piece_logcdf(ig, h, s2x, x, z);  // the reference's lgamma(h) cancels
+    // ratios F_n / F_0 are formed in linear space only while both are comfortably normal numbers
+    double F0 = 0.0;
+    const bool linear = h <= 300.0 && first > -600.0 && piece_cdf_fast(ig, h, s2x, half_rsx, zsx, F0);
+    double ck = linear ? 1.0 / F0 : 1.0;  // Gamma(n+h) / (Gamma(h) n!) e^{-n z} / F_0
+    double lc = 0.0;
+    double sum = 1.0, sign = -1.0, prev_term = 1.0;
     for (int n = 1; n < kMaxSeriesTerms; ++n, sign = -sign) {
-        double dn = (double)n;
-        lc += log((dn - 1.0 + h) / dn);
-        double curr = lc + piece_logcdf(ig, 2.0 * dn + h, s2x, x, z) - z * dn;
-        sum += sign * exp(curr - first);
+        const double dn = (double)n;
+        const double a = 2.0 * dn + h;
+        double F;
+        double term;
+        if (linear) {
+            ck *= (dn - 1.0 + h) / dn * ez;
+            term = (piece_cdf_fast(ig, a, s2x, half_rsx, zsx, F) && F > 1e-280)
+                       ? ck * F
+                       : exp(log(ck) + piece_logcdf(ig, a, s2x, x, z));
+        }
+        else {
+            lc += log((dn - 1.0 + h) / dn);
+            term = exp(lc + piece_logcdf(ig, a, s2x, x, z) - z * dn - first);
+        }
+        sum += sign * term;
+        // same argument as in pg_logpdf: later terms cannot change the sum any more
+        if (term < prev_term && term <= 1e-30 * fabs(sum)) break;
+        prev_term = term;
     }
     return c + (first + log(sum));
 }
