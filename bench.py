@@ -37,14 +37,15 @@ METRIC = "PG(h,z) samples/sec at 1/2/4/8 B200 (hybrid, mixed h,z); % of roofline
 UNIT = "samples/s"
 WORKLOAD = "cfg4: fill2 hybrid, h~U[0.1,200], z~U[-50,50] (BASELINE.json configs[3])"
 
-# Algorithmic FP64 flops per element of each method kernel on the cfg4 distribution
-# (2 x DFMA + DMUL + DADD executed per element; fill2, i.e. including the per-element setup).
-# Provenance: ncu `smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on.sum` of the kernels
-# in profiles/ divided by the elements of that launch -- see DESIGN.md "Roofline accounting";
-# SURVEY 8(d)'s nominal figures are kept beside them there.
-FLOPS_PER_ELEMENT = {"devroye": 6.0e2, "alternate": 1.5e3, "alternate_left": 6.0e2, "setup_alternate_left": 2.0, "saddle": 2.0e3, "saddle_left": 7.0e2, "saddle_far": 5.0e2,
-                     "normal": 1.45e2, "gamma": 6.0e4, "setup_devroye": 4.0e2, "setup_alternate": 2.5e3,
-                     "setup_saddle": 5.0e3, "setup_saddle_left": 4.5e2, "setup_saddle_far": 3.0e2}
+# FP64 flops per element of each kernel on the cfg4 distribution: executed thread-level
+# instructions 2*DFMA + DMUL + DADD (ncu smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on)
+# of one profiled launch divided by the elements of that launch -- profiles/r1f_cfg4_all_kernels.txt,
+# table in profiles/README.md (SURVEY 8(d)'s nominal per-method figures are kept beside them there).
+# devroye figures are from the cfg2 capture (cfg4 has no devroye elements).
+FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 593.0, "alternate_left": 441.0, "saddle": 636.0,
+                     "saddle_left": 675.0, "saddle_far": 328.0, "normal": 145.0, "gamma": 6.0e4,
+                     "setup_devroye": 356.0, "setup_alternate": 1223.0, "setup_alternate_left": 1.0,
+                     "setup_saddle": 1737.0, "setup_saddle_left": 363.0, "setup_saddle_far": 294.0}
 KERNEL_NAMES = {"devroye": "sample_kernel<Devroye>", "alternate": "sample_kernel<Alternate>",
                 "alternate_left": "sample_kernel<AlternateLeft>", "setup_alternate_left": "setup_kernel<AlternateLeft>",
                 "saddle": "sample_kernel<SaddleFull>", "saddle_left": "sample_kernel<SaddleLeft>",
