@@ -353,11 +353,13 @@ __global__ void __launch_bounds__(kBucketThreads)
 scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __restrict__ block_offsets,
                const uint32_t* __restrict__ ctl, uint32_t* __restrict__ list)
 {
+    static_assert(kNumBuckets <= 8 && kPacked == 4, "offsets are packed 4 x 16 bit into two 64-bit words");
     __shared__ uint32_t s_warp[kBucketThreads / 32][kPacked];
+    __shared__ uint32_t s_run[8];  // next free list slot of each bucket for this block
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t run[kNumBuckets];  // next free list slot of each bucket for this block
-#pragma unroll
-    for (int q = 0; q < kNumBuckets; ++q) run[q] = ctl[kCtlBase + q] + block_offsets[q * gridDim.x + blockIdx.x];
+    if (threadIdx.x < kNumBuckets) {
+        s_run[threadIdx.x] = ctl[kCtlBase + threadIdx.x] + block_offsets[threadIdx.x * gridDim.x + blockIdx.x];
+    }
     for (int tile = 0; tile < kTilesPerBlock; ++tile) {
         const uint32_t t0 = (blockIdx.x * kTilesPerBlock + tile) * kBucketTile;
         if (t0 >= n) break;  // block-uniform
@@ -367,6 +369,7 @@ scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __r
             word = *reinterpret_cast<const uint64_t*>(meth + e0);
         }
         else {
+#pragma unroll
             for (int k = 0; k < kBucketItems; ++k) {
                 if (e0 + k < n) word = (word & ~(0xffull << (8 * k))) | ((uint64_t)meth[e0 + k] << (8 * k));
             }
@@ -387,7 +390,7 @@ scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __r
             incl[w] = v;
             if (lane == 31) s_warp[warp][w] = v;
         }
-        __syncthreads();
+        __syncthreads();  // s_warp of this tile and s_run of the previous tile are visible
         uint32_t before[kPacked], total[kPacked];
 #pragma unroll
         for (int w = 0; w < kPacked; ++w) {
@@ -400,16 +403,28 @@ scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __r
             before[w] = bsum + incl[w] - pc[w];  // elements of this tile ahead of this thread
             total[w] = tsum;
         }
+        // per-item destination: bucket base (shared memory) + this thread's running 16-bit offset
+        // of that bucket, kept four to a 64-bit word
+        uint64_t lo = (uint64_t)before[0] | ((uint64_t)before[1] << 32);
+        uint64_t hi = (uint64_t)before[2] | ((uint64_t)before[3] << 32);
+#pragma unroll
+        for (int k = 0; k < kBucketItems; ++k) {
+            const uint32_t q = (uint32_t)(word >> (8 * k)) & 0xffu;
+            if (q < (uint32_t)kNumBuckets) {
+                const uint32_t sh = (q & 3u) * 16u;
+                const uint64_t sel = (q & 4u) ? hi : lo;
+                list[s_run[q] + (uint32_t)((sel >> sh) & 0xffffu)] = e0 + k;
+                if (q & 4u) hi += 1ull << sh;
+                else lo += 1ull << sh;
+            }
+        }
+        __syncthreads();  // every thread has read s_run
+        uint32_t mine = 0;
 #pragma unroll
         for (int q = 0; q < kNumBuckets; ++q) {
-            uint32_t o = run[q] + packed_get(before, q);
-#pragma unroll
-            for (int k = 0; k < kBucketItems; ++k) {
-                if (((word >> (8 * k)) & 0xff) == (uint64_t)q) list[o++] = e0 + k;
-            }
-            run[q] += packed_get(total, q);
+            if (threadIdx.x == (uint32_t)q) mine = packed_get(total, q);
         }
-        __syncthreads();
+        if (threadIdx.x < kNumBuckets) s_run[threadIdx.x] += mine;
     }
 }
 
