@@ -676,8 +676,8 @@ struct SaddleT {
     using Rng = RngFor<(MODE == kSaddleFull ? 2 : MODE == kSaddleLeft ? 3 : 4)>;
     static constexpr bool FULL = (MODE == kSaddleFull);
     static constexpr bool FAR = (MODE == kSaddleFar);
-    // h, zz, xl, c_l, a1, a2 [, w_left, c_r, slope_r]
-    static constexpr int kFields = FULL ? 9 : 6;
+    // h, zz, xl, c_l [, a1, a2 [, w_left, c_r, slope_r]]  (the far kernel never uses the expansion)
+    static constexpr int kFields = FULL ? 9 : FAR ? 4 : 6;
 
     struct Par {
         double h, half_z2, xl, xc, slope_l, c_l, a1, a2;
@@ -715,27 +715,29 @@ struct SaddleT {
         const double alpha_r = fp_c * xc_inv * xc_inv;  // K2(u(xc)) / xc^2, K2 = second derivative
         const double alpha_l = xc_inv * alpha_r;
         const double icpt_l = -0.5 * xc_inv + xl_inv;  // cumulant(ul) = 0, src/pgm_saddle.c:216
-        // second-order expansion of u(x) about x = xl, where u = -zz^2/2 and K1(u) = xl exactly:
-        // du/dx = 1 / K2, d2u/dx2 = -K3 / K2^3  (K1, K2, K3 = derivatives of the cumulant)
-        double fp_l, fpp_l;
-        if (zz * zz < 1e-4) {
-            double f_l;
-            kprime3(-half_z2, f_l, fp_l, fpp_l);
-        }
-        else {
-            const double inv = -1.0 / (zz * zz);
-            const double t = (1.0 - xl) * inv;
-            fp_l = xl * xl + t;
-            fpp_l = 2.0 * xl * fp_l - fp_l * inv - 2.0 * t * inv;
-        }
-        const double a1 = 1.0 / fp_l;
         rec[0] = h;
         rec[1] = zz;
         rec[2] = xl;
         // constant part of  log k_l(x) - log phi(x)  (bounding_kernel :250-263, saddle_point :235-244)
         rec[3] = 0.5 * h * xc_inv + h * icpt_l - 0.5 * log(alpha_l) - h * log_cosh_z;
-        rec[4] = a1;
-        rec[5] = -0.5 * fpp_l * a1 * a1 * a1;
+        if (!FAR) {
+            // second-order expansion of u(x) about x = xl, where u = -zz^2/2 and K1(u) = xl exactly:
+            // du/dx = 1 / K2, d2u/dx2 = -K3 / K2^3  (K1, K2, K3 = derivatives of the cumulant)
+            double fp_l, fpp_l;
+            if (zz * zz < 1e-4) {
+                double f_l;
+                kprime3(-half_z2, f_l, fp_l, fpp_l);
+            }
+            else {
+                const double inv = -1.0 / (zz * zz);
+                const double t = (1.0 - xl) * inv;
+                fp_l = xl * xl + t;
+                fpp_l = 2.0 * xl * fp_l - fp_l * inv - 2.0 * t * inv;
+            }
+            const double a1 = 1.0 / fp_l;
+            rec[4] = a1;
+            rec[5] = -0.5 * fpp_l * a1 * a1 * a1;
+        }
         if (FULL) {
             const double logxl = log(xl);
             const double xr = 3.0 * xl;
@@ -770,8 +772,10 @@ struct SaddleT {
         p.xc = 2.75 * p.xl;
         p.slope_l = -0.5 / (p.xl * p.xl);
         p.c_l = rec[3];
-        p.a1 = rec[4];
-        p.a2 = rec[5];
+        if (!FAR) {
+            p.a1 = rec[4];
+            p.a2 = rec[5];
+        }
         if (FULL) {
             p.w_left = rec[6];
             p.c_r = rec[7];
@@ -832,9 +836,8 @@ struct SaddleT {
             if (x <= 0.25) {
                 u0 = asymptotic_guess(x);
             }
-            else if (fabs(d) <= 0.5 * p.xl) {
-                u0 = -p.half_z2 + d * (p.a1 + p.a2 * d);
-                u0 = FAR ? fmin(u0, -1e-3) : fmin(u0, kUMax - 1e-3);
+            else if (!FAR && fabs(d) <= 0.5 * p.xl) {
+                u0 = fmin(-p.half_z2 + d * (p.a1 + p.a2 * d), kUMax - 1e-3);
             }
             else {
                 u0 = table_guess(x);

@@ -578,7 +578,32 @@ __global__ void __launch_bounds__(256)
 dense_kernel(FillArgs a, Bucket b)
 {
     const BucketView v = view_of(b);
-    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < v.count; pos += gridDim.x * blockDim.x) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    if (KIND == kNormal) {
+        // two elements per trip: both gathers (list index -> h, z) are in flight before either
+        // element's arithmetic starts, and the two dependency chains interleave
+        for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < v.count; pos += 2 * stride) {
+            const uint32_t pos1 = pos + stride;
+            const bool two = pos1 < v.count;
+            const uint32_t e0 = v.list ? v.list[pos] : pos;
+            const uint32_t e1 = two ? (v.list ? v.list[pos1] : pos1) : e0;
+            const uint64_t g0 = a.base + e0, g1 = a.base + e1;
+            double h0, z0, h1, z1, bad;
+            load_hz(a, g0, h0, z0);
+            load_hz(a, g1, h1, z1);
+            RngInline r0, r1;
+            r0.init(a.key, a.first_index + g0);
+            r1.init(a.key, a.first_index + g1);
+            const double s0 = invalid_h(h0, bad) ? bad : normal_approx_sample(r0, h0, z0);
+            a.out[g0] = s0;
+            if (two) {
+                const double s1 = invalid_h(h1, bad) ? bad : normal_approx_sample(r1, h1, z1);
+                a.out[g1] = s1;
+            }
+        }
+        return;
+    }
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < v.count; pos += stride) {
         uint32_t e = v.list ? v.list[pos] : pos;
         uint64_t g = a.base + e;
         double h, z, bad;
@@ -587,16 +612,9 @@ dense_kernel(FillArgs a, Bucket b)
             a.out[g] = bad;
             continue;
         }
-        if (KIND == kNormal) {
-            RngInline rng;
-            rng.init(a.key, a.first_index + g);
-            a.out[g] = normal_approx_sample(rng, h, z);
-        }
-        else {
-            GammaRng rng;
-            rng.init(a.key, a.first_index + g);
-            a.out[g] = gamma_conv_sample(rng, h, z);
-        }
+        GammaRng rng;
+        rng.init(a.key, a.first_index + g);
+        a.out[g] = gamma_conv_sample(rng, h, z);
     }
 }
 

@@ -165,6 +165,21 @@ def test_return_types_and_out_semantics(pg):
 
     res2 = pg.random_polyagamma(CAI(h), 1.0, random_state=(1, 1))
     assert torch.equal(res, res2)
+
+    class DLP:  # a foreign array that only speaks DLPack
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, **kw):
+            return self.t.__dlpack__(**kw)
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    res3 = pg.random_polyagamma(DLP(h), 1.0, random_state=(1, 1))
+    assert isinstance(res3, torch.Tensor) and torch.equal(res, res3)
+    d1 = pg.polyagamma_pdf(DLP(res), CAI(h), 1.0)
+    assert d1.is_cuda and torch.equal(d1, pg.polyagamma_pdf(res, h, 1.0))
     dout = torch.zeros(6, dtype=torch.float64, device="cuda")
     assert pg.random_polyagamma(h, 1.0, out=dout, random_state=(1, 1)) is dout
     assert torch.equal(dout, res)

@@ -174,6 +174,54 @@ def test_hybrid_equals_explicit_methods_full_size(pg, torch):
     torch.cuda.empty_cache()
 
 
+def _pit_ks(pg, torch, x, h, z):
+    """sqrt(n) * KS distance of the probability integral transform cdf(x_i; h_i, z_i) from U(0,1)."""
+    u = pg.polyagamma_cdf(x, h, z)
+    u, _ = torch.sort(u)
+    n = u.numel()
+    i = torch.arange(1, n + 1, device=u.device, dtype=torch.float64)
+    d = max(float((i / n - u).max()), float((u - (i - 1) / n).max()))
+    return d * np.sqrt(n)
+
+
+def test_cfg2_full_size_pit_and_moments(pg, torch):
+    """BASELINE cfg2 at full size: 1e8 draws of PG(1, z_i), z ~ N(0, 3) (the logistic-regression
+    Gibbs omega-step), scalar h broadcast against the z array.  Size-independent checks: the
+    probability integral transform through polyagamma_cdf is uniform (KS at n = 1e8), and the
+    standardised sum of (omega_i - E omega_i) is N(0, 1)."""
+    n = 100_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(20240)
+    z = torch.randn(n, device="cuda", dtype=torch.float64, generator=g) * 3
+    x = pg.random_polyagamma(1.0, z, random_state=(12345, 0), disable_checks=True)
+    assert x.shape == (n,) and bool((x > 0).all()) and bool(torch.isfinite(x).all())
+    za = z.abs().clamp_min(1e-8)
+    mean = torch.tanh(za / 2) / (2 * za)
+    var = (torch.sinh(za) - za) / torch.cosh(za / 2) ** 2 / (4 * za**3)
+    var = torch.where(za < 1e-2, torch.full_like(za, 1 / 24.0), var)
+    zscore = float((x - mean).sum() / var.sum().sqrt())
+    assert abs(zscore) < 4.0, zscore
+    del mean, var, za
+    assert _pit_ks(pg, torch, x, 1.0, z) < 1.95
+    del x, z
+    torch.cuda.empty_cache()
+
+
+def test_cfg3_alternate_full_size_pit(pg, torch):
+    """BASELINE cfg3 alternate sweep at full size: h ~ U[1, 4], z ~ U[-50, 50], 1e8 elements,
+    explicit method (both the full and the left-only kernels are exercised)."""
+    n = 100_000_000
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    h = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 3 + 1
+    z = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 100 - 50
+    x = pg.random_polyagamma(h, z, method="alternate", random_state=(12345, 1), disable_checks=True)
+    assert bool((x > 0).all()) and bool(torch.isfinite(x).all())
+    assert _pit_ks(pg, torch, x, h, z) < 1.95
+    del x, h, z
+    torch.cuda.empty_cache()
+
+
 def test_invalid_h_and_edge_sizes(pg, torch):
     h = _cuda(torch, [1.0, -1.0, 0.0, np.nan, np.inf, -np.inf, 2.0, 60.0, 9.0])
     z = torch.zeros_like(h)
