@@ -39,13 +39,13 @@ WORKLOAD = "cfg4: fill2 hybrid, h~U[0.1,200], z~U[-50,50] (BASELINE.json configs
 
 # FP64 flops per element of each kernel on the cfg4 distribution: executed thread-level
 # instructions 2*DFMA + DMUL + DADD (ncu smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on)
-# of one profiled launch divided by the elements of that launch -- profiles/r1f_cfg4_all_kernels.txt,
+# of one profiled launch divided by the elements of that launch -- profiles/r1g_cfg4_all_kernels.txt,
 # table in profiles/README.md (SURVEY 8(d)'s nominal per-method figures are kept beside them there).
 # devroye figures are from the cfg2 capture (cfg4 has no devroye elements).
-FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 593.0, "alternate_left": 441.0, "saddle": 636.0,
-                     "saddle_left": 675.0, "saddle_far": 328.0, "normal": 145.0, "gamma": 6.0e4,
-                     "setup_devroye": 356.0, "setup_alternate": 1223.0, "setup_alternate_left": 1.0,
-                     "setup_saddle": 1737.0, "setup_saddle_left": 363.0, "setup_saddle_far": 294.0}
+FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 596.0, "alternate_left": 383.0, "saddle": 602.0,
+                     "saddle_left": 642.0, "saddle_far": 298.0, "normal": 150.0, "gamma": 6.0e4,
+                     "setup_devroye": 356.0, "setup_alternate": 1222.0, "setup_alternate_left": 1.0,
+                     "setup_saddle": 1790.0, "setup_saddle_left": 363.0, "setup_saddle_far": 269.0}
 KERNEL_NAMES = {"devroye": "sample_kernel<Devroye>", "alternate": "sample_kernel<Alternate>",
                 "alternate_left": "sample_kernel<AlternateLeft>", "setup_alternate_left": "setup_kernel<AlternateLeft>",
                 "saddle": "sample_kernel<SaddleFull>", "saddle_left": "sample_kernel<SaddleLeft>",

@@ -126,6 +126,10 @@ int pgm_cuda_profile_end(double* ms, uint64_t* launches, int cap);
 /* FP64 (DFMA) peak of the current device in TFLOP/s, measured by a register-resident FMA
  * microbenchmark: the denominator of the FP64 roofline.  Synchronises `stream`. */
 int pgm_cuda_fp64_peak_tflops(double* tflops, void* stream);
+/* Unit-test hook: applies one of the kernels' own elementary functions (csrc/pgm_device.cuh, fm::)
+ * elementwise.  which: 0 rcp, 1 sqrt, 2 log, 3 exp, 4 cos(2 pi x), 5 rsqrt, 6 sin(2 pi x) and
+ * 7 cos(2 pi x) of the paired routine, 8 1/x by fm::div. */
+int pgm_cuda_test_math(int which, const double* d_in, size_t n, double* d_out, void* stream);
 /* "polyagamma_b200 <version> sm_100a" */
 const char* pgm_cuda_version(void);
 /* Method the hybrid sampler picks for (h, z): 0 gamma, 1 devroye, 2 alternate, 3 saddle,

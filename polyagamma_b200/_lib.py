@@ -35,6 +35,7 @@ EXPORTS = (
     "pgm_cuda_profile_begin",
     "pgm_cuda_profile_end",
     "pgm_cuda_fp64_peak_tflops",
+    "pgm_cuda_test_math",
     "pgm_cuda_version",
     "pgm_cuda_hybrid_select",
     "pgm_cuda_call_key",
@@ -87,6 +88,8 @@ def lib() -> ctypes.CDLL:
     L.pgm_cuda_profile_end.argtypes = [ctypes.POINTER(d), ctypes.POINTER(u64), i]
     L.pgm_cuda_fp64_peak_tflops.restype = i
     L.pgm_cuda_fp64_peak_tflops.argtypes = [ctypes.POINTER(d), vp]
+    L.pgm_cuda_test_math.restype = i
+    L.pgm_cuda_test_math.argtypes = [i, vp, sz, vp, vp]
     L.pgm_cuda_version.restype = ctypes.c_char_p
     L.pgm_cuda_version.argtypes = []
     L.pgm_cuda_hybrid_select.restype = i

@@ -11,7 +11,22 @@
 #include "pgm_internal.h"
 #include "pgm_methods.cuh"
 
-using namespace pgm;
+// (no `using namespace pgm`: that namespace re-declares log/exp/sqrt for the kernels)
+using pgm::DensityArgs;
+using pgm::FillArgs;
+using pgm::PhiloxKey;
+using pgm::derive_call_key;
+using pgm::hybrid_select;
+using pgm::kDevroye;
+using pgm::kMaxNdim;
+using pgm::launch_check_h;
+using pgm::launch_count;
+using pgm::launch_density;
+using pgm::launch_fill;
+using pgm::launch_test_math;
+using pgm::measure_fp64_peak;
+using pgm::profile_begin;
+using pgm::profile_end;
 
 namespace {
 
@@ -110,6 +125,13 @@ pgm_cuda_fp64_peak_tflops(double* tflops, void* stream)
 {
     if (tflops == nullptr) return PGM_CUDA_EINVAL;
     return measure_fp64_peak(tflops, (cudaStream_t)stream);
+}
+
+int
+pgm_cuda_test_math(int which, const double* d_in, size_t n, double* d_out, void* stream)
+{
+    if (n != 0 && (d_in == nullptr || d_out == nullptr)) return PGM_CUDA_EINVAL;
+    return launch_test_math(which, d_in, n, d_out, (cudaStream_t)stream);
 }
 
 int

@@ -58,6 +58,181 @@ derive_call_key(uint64_t seed, uint64_t offset)
 
 #ifdef __CUDACC__
 
+// ---------------------------------------------------------------------------------------
+// fm:: -- lean FP64 elementary functions for the sampling kernels.
+//
+// ncu showed ~70 % of the instructions of the sampling kernels are not FP64: libdevice's
+// log/exp/cospi/division/sqrt spend most of their issue slots on special-case tests, exponent
+// bookkeeping and UMOV pairs that materialise every 64-bit polynomial coefficient.  These versions
+// assume the arguments the samplers actually produce (finite, normal; anything else falls back to
+// libdevice), take their coefficients from __constant__ memory (two doubles per LDCU.128) and
+// replace IEEE division / square root by MUFU seeds with two Newton steps.  Accuracy (checked in
+// tests/test_gpu_parity.py::test_fast_math): log, exp <= 2 ulp; rcp, sqrt <= 1 ulp; cos(2 pi u)
+// <= 1e-15 absolute.  Polynomials: fdlibm e_log.c (Lg1..Lg7), k_sin.c / k_cos.c; exp: degree-13
+// Taylor on |r| <= ln2/2.
+// ---------------------------------------------------------------------------------------
+namespace fm {
+
+static __constant__ double c_log[8] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                                       2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                                       1.479819860511658591e-01, 0.0};
+static __constant__ double c_exp[14] = {1.0,
+                                        1.0,
+                                        0.5,
+                                        1.6666666666666666e-01,
+                                        4.1666666666666664e-02,
+                                        8.3333333333333332e-03,
+                                        1.3888888888888889e-03,
+                                        1.9841269841269841e-04,
+                                        2.4801587301587302e-05,
+                                        2.7557319223985893e-06,
+                                        2.7557319223985888e-07,
+                                        2.5052108385441720e-08,
+                                        2.0876756987868100e-09,
+                                        1.6059043836821613e-10};
+static __constant__ double c_sin[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03,
+                                       -1.98412698298579493134e-04, 2.75573137070700676789e-06,
+                                       -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+static __constant__ double c_cos[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03,
+                                       2.48015872894767294178e-05,  -2.75573143513906633035e-07,
+                                       2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+constexpr double kLn2Hi = 6.93147180369123816490e-01;
+constexpr double kLn2Lo = 1.90821492927058770002e-10;
+
+// 1/x for finite normal x: MUFU.RCP64H seed (~20 bits) + two Newton steps
+__device__ __forceinline__ double
+rcp(double x)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+// a/b with one residual correction (result within 1 ulp)
+__device__ __forceinline__ double
+div(double a, double b)
+{
+    const double r = rcp(b);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+}
+
+// 1/sqrt(x) and sqrt(x) for finite normal x > 0: MUFU.RSQ64H seed + two Newton steps
+__device__ __forceinline__ double
+rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
+}
+
+__device__ __forceinline__ double
+sqrt(double x)
+{
+    if (!(x > 2.3e-308)) return ::sqrt(x);  // zero, denormal, negative, NaN
+    const double y = rsqrt(x);
+    const double s = x * y;
+    return fma(fma(-s, s, x), 0.5 * y, s);
+}
+
+// natural logarithm of a finite normal x > 0 (anything else: libdevice)
+__device__ __forceinline__ double
+log(double x)
+{
+    if (!(x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308)) return ::log(x);
+    const long long bits = __double_as_longlong(x);
+    int e = (int)(bits >> 52) - 1023;
+    double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);  // [1, 2)
+    if (m > 1.4142135623730951) {
+        m *= 0.5;
+        e += 1;
+    }
+    const double f = m - 1.0;
+    const double s = f * rcp(2.0 + f);
+    const double z = s * s;
+    double R = c_log[6];
+#pragma unroll
+    for (int k = 5; k >= 0; --k) R = fma(R, z, c_log[k]);
+    R *= z;
+    const double hfsq = 0.5 * f * f;
+    const double de = (double)e;
+    return de * kLn2Hi - ((hfsq - (s * (hfsq + R) + de * kLn2Lo)) - f);
+}
+
+// e^x for x <= 700; x < -707 flushes to 0 (the samplers never need denormal results)
+__device__ __forceinline__ double
+exp(double x)
+{
+    if (!(x <= 700.0)) return ::exp(x);  // huge or NaN
+    if (x < -707.0) return 0.0;
+    // n = round(x / ln 2) by the 1.5 * 2^52 trick: the integer lands in the low word
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int n = __double2loint(t);
+    const double dn = t - 6755399441055744.0;
+    double r = fma(dn, -kLn2Hi, x);
+    r = fma(dn, -kLn2Lo, r);
+    double p = c_exp[13];
+#pragma unroll
+    for (int k = 12; k >= 0; --k) p = fma(p, r, c_exp[k]);
+    // scale by 2^n (|n| <= 1022 here): add n to the exponent field
+    return __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));
+}
+
+// cos(2 pi u) for u in [0, 1]: quadrant from round(4u), sine/cosine kernels on [-pi/4, pi/4]
+__device__ __forceinline__ double
+cos2pi(double u)
+{
+    const double v = 4.0 * u;
+    const double t = v + 6755399441055744.0;
+    const int q = __double2loint(t);
+    const double r = v - (t - 6755399441055744.0);
+    const double y = r * 1.5707963267948966;
+    const double y2 = y * y;
+    double sn = c_sin[5], cs = c_cos[5];
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+        sn = fma(sn, y2, c_sin[k]);
+        cs = fma(cs, y2, c_cos[k]);
+    }
+    sn = fma(y * y2, sn, y);
+    cs = fma(y2 * y2, cs, fma(-0.5, y2, 1.0));
+    const double val = (q & 1) ? sn : cs;
+    return ((q + 1) & 2) ? -val : val;  // q: 0 -> cos, 1 -> -sin, 2 -> -cos, 3 -> sin, 4 -> cos
+}
+
+// sin and cos of 2 pi u together (Box-Muller pairs)
+__device__ __forceinline__ void
+sincos2pi(double u, double& s_out, double& c_out)
+{
+    const double v = 4.0 * u;
+    const double t = v + 6755399441055744.0;
+    const int q = __double2loint(t);
+    const double r = v - (t - 6755399441055744.0);
+    const double y = r * 1.5707963267948966;
+    const double y2 = y * y;
+    double sn = c_sin[5], cs = c_cos[5];
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+        sn = fma(sn, y2, c_sin[k]);
+        cs = fma(cs, y2, c_cos[k]);
+    }
+    sn = fma(y * y2, sn, y);
+    cs = fma(y2 * y2, cs, fma(-0.5, y2, 1.0));
+    // angle = (pi/2)(q + r): rotate by q quadrants
+    const double c0 = (q & 1) ? sn : cs, s0 = (q & 1) ? cs : sn;
+    c_out = ((q + 1) & 2) ? -c0 : c0;
+    s_out = (q & 2) ? -s0 : s0;
+}
+
+}  // namespace fm
+
 // One private stream per output element: words of Philox(call key, ctr = (idx, block, 0)),
 // block = 0, 1, 2, ..., consumed strictly in order.  The four buffered words live in
 // registers and are shifted down on every draw (no local-memory indexing).
@@ -121,22 +296,22 @@ struct RngT {
     // (0, 1]
     __device__ __forceinline__ double uniform_oc() { return ((double)u53() + 1.0) * 1.1102230246251565e-16; }
     // replaces numpy random_standard_exponential
-    __device__ __forceinline__ double exponential() { return -log(uniform_oc()); }
+    __device__ __forceinline__ double exponential() { return -fm::log(uniform_oc()); }
     // replaces numpy random_standard_normal: one Box-Muller draw (4 words)
     __device__ __forceinline__ double normal()
     {
         double u1 = uniform_oc();
         double u2 = uniform_co();
-        return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        return fm::sqrt(-2.0 * fm::log(u1)) * fm::cos2pi(u2);
     }
     // Box-Muller pair (used by the gamma-convolution sampler)
     __device__ __forceinline__ void normal_pair(double& n0, double& n1)
     {
         double u1 = uniform_oc();
         double u2 = uniform_co();
-        double rad = sqrt(-2.0 * log(u1));
+        double rad = fm::sqrt(-2.0 * fm::log(u1));
         double s, c;
-        sincospi(2.0 * u2, &s, &c);
+        fm::sincos2pi(u2, s, c);
         n0 = rad * c;
         n1 = rad * s;
     }

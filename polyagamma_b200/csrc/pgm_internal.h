@@ -51,6 +51,7 @@ int launch_density(int which, DensityArgs a, uint64_t n, cudaStream_t s);
 uint64_t launch_count();
 void count_launch(uint64_t n);
 int measure_fp64_peak(double* tflops, cudaStream_t s);
+int launch_test_math(int which, const double* d_in, size_t n, double* d_out, cudaStream_t s);
 
 // kernel kinds reported by pgm_cuda_profile_end
 enum : int {

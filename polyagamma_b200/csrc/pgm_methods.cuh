@@ -26,6 +26,12 @@
 
 namespace pgm {
 
+// Unqualified log / exp / sqrt in this header are the lean fm:: versions (same results to ~1 ulp
+// for finite normal arguments, libdevice fallback otherwise).
+using fm::exp;
+using fm::log;
+using fm::sqrt;
+
 constexpr int kMaxRecordFields = 9;  // saddle-full is the largest record
 
 // Which sampling kernels keep a single out-of-line copy of the Philox block function (bit i =
@@ -47,9 +53,10 @@ struct Devroye {
 
     struct Par {
         double w;   // p / (p + q): probability of the truncated inverse-Gaussian piece
-        double K;
+        double inv_K;
         double zz;  // |z| / 2
         double z2;
+        double mu2;  // 1 / z2
     };
     struct State {
         double acc;
@@ -90,9 +97,10 @@ struct Devroye {
     static __device__ __forceinline__ bool load(const Rec& rec, Par& p, State& s, bool)
     {
         p.w = rec[0];
-        p.K = rec[1];
+        p.inv_K = fm::rcp(rec[1]);
         p.zz = rec[2];
         p.z2 = p.zz * p.zz;
+        p.mu2 = (p.zz > 0.0) ? fm::rcp(p.z2) : 0.0;
         s.acc = 0.0;
         s.remaining = (uint32_t)rec[3];
         s.in_left = 0;
@@ -124,24 +132,24 @@ struct Devroye {
                 const double e2 = r.exponential();
                 if (L * L > 3.125 * e2) return false;
                 x = 1.0 + T * L;
-                x = T / (x * x);
+                x = T * fm::rcp(x * x);
                 if (p.zz > 0.0 && !(r.uniform32() < exp(-0.5 * p.z2 * x))) return false;
             }
             else {  // IG(1/z, 1) by Michael-Schucany-Haas; only the square of the normal is needed
-                const double c = cospi(2.0 * r.uniform_co());
+                const double c = fm::cos2pi(r.uniform_co());
                 const double y2 = 2.0 * L * c * c;
-                const double mu2 = 1.0 / p.z2;
+                const double mu2 = p.mu2;
                 const double w = (p.zz + 0.5 * y2) * mu2;
-                x = mu2 / (w + sqrt(fmax(w * w - mu2, 0.0)));
+                x = mu2 * fm::rcp(w + sqrt(fmax(w * w - mu2, 0.0)));
                 if (r.uniform_co() * (1.0 + x * p.zz) > 1.0) {
-                    x = mu2 / x;
+                    x = mu2 * fm::rcp(x);
                 }
                 if (x >= T) return false;
             }
             s.in_left = 0;
         }
         else {
-            x = T + L / p.K;
+            x = T + L * p.inv_K;
         }
         if (x > T) {
             lp = 0.0;
@@ -149,7 +157,7 @@ struct Devroye {
         }
         else {
             lp = -1.5 * (kLogPi_2 + log(x));
-            e = 2.0 / x;
+            e = 2.0 * fm::rcp(x);
         }
         double sum = coef(0, lp, e);
         double u = r.uniform32() * sum;
@@ -416,7 +424,7 @@ struct AlternateLeft {
     static constexpr int kFields = 2;  // h, zz
 
     struct Par {
-        double h, zz, z2, t, half_h2, hlog2, h_z, h_z2;
+        double h, zz, inv_z2, t, half_h2, hlog2, h_z, h_z2;
     };
     struct State {
         double acc;
@@ -437,8 +445,9 @@ struct AlternateLeft {
         p.t = Alternate::trunc_point(h);
         p.half_h2 = 0.5 * h * h;
         p.hlog2 = h * kLog2;
-        p.z2 = zz * zz;
-        p.h_z = h / zz;
+        const double inv_z = fm::rcp(zz);
+        p.inv_z2 = inv_z * inv_z;
+        p.h_z = h * inv_z;
         p.h_z2 = p.h_z * p.h_z;
     }
 
@@ -467,15 +476,15 @@ struct AlternateLeft {
         double x;
         do {
             double y = r.normal();
-            double w = p.h_z + 0.5 * y * y / p.z2;
-            x = p.h_z2 / (w + sqrt(fmax(w * w - p.h_z2, 0.0)));
+            double w = p.h_z + 0.5 * y * y * p.inv_z2;
+            x = p.h_z2 * fm::rcp(w + sqrt(fmax(w * w - p.h_z2, 0.0)));
             if (r.uniform_co() * (p.h_z + x) > p.h_z) {
-                x = p.h_z2 / x;
+                x = p.h_z2 * fm::rcp(x);
             }
         } while (x >= p.t);
         const double logx = log(x);
         const double base = p.hlog2 - kLs2Pi - 1.5 * logx;
-        const double inv2x = 0.5 / x;
+        const double inv2x = 0.5 * fm::rcp(x);
         // k(x) = a_0(x) on the left of t: u = U * a_0
         double a_prev = p.h * exp(base - p.h * p.h * inv2x);
         const double u = r.uniform32() * a_prev;
@@ -484,7 +493,7 @@ struct AlternateLeft {
         bool accept = false;
         for (int n = 1; n < 2000; ++n) {
             double tn = 2.0 * n + p.h;
-            c *= (n - 1.0 + p.h) / n;
+            c *= (n - 1.0 + p.h) * fm::rcp((double)n);
             double a = c * tn * exp(base - tn * tn * inv2x);
             if (n & 1) {
                 sum -= a;
@@ -543,10 +552,19 @@ kprime3(double u, double& f, double& fp, double& fpp)
         return;
     }
     double a = fabs(s2);
-    double rs = rsqrt(a);
+    double rs = fm::rsqrt(a);
     double s = a * rs;
     double inv = (!NEG && s2 > 0.0) ? rs * rs : -(rs * rs);
-    f = ((!NEG && s2 > 0.0) ? tan(s) : tanh(s)) * rs;
+    double tt;
+    if (!NEG && s2 > 0.0) {
+        tt = tan(s);
+    }
+    else {
+        // tanh s = (1 - e^{-2s}) / (1 + e^{-2s}); below s = 0.1 the subtraction would cost digits
+        const double e2 = fm::exp(-2.0 * s);
+        tt = (s < 0.1) ? tanh(s) : (1.0 - e2) * fm::rcp(1.0 + e2);
+    }
+    f = tt * rs;
     double t = (1.0 - f) * inv;
     fp = f * f + t;
     fpp = 2.0 * f * fp - fp * inv - 2.0 * t * inv;
@@ -568,7 +586,7 @@ cumulant0(double u, double f)
         if (s < 3.0) {
             return 0.5 * log((1.0 - th) * (1.0 + th));
         }
-        double e = (1.0 - th) / (1.0 + th);  // e^{-2s}
+        double e = (1.0 - th) * fm::rcp(1.0 + th);  // e^{-2s}
         return -(s - kLog2 + e * (1.0 - e * (0.5 - e * (1.0 / 3.0 - 0.25 * e))));
     }
     return 0.0;
@@ -581,7 +599,7 @@ cumulant0(double u, double f)
 __device__ __forceinline__ double
 asymptotic_guess(double x)
 {
-    const double xi = 1.0 / x;
+    const double xi = fm::rcp(x);
     const double e = exp(-2.0 * xi);
     const double s = (1.0 - 2.0 * e + e * e * (2.0 - 8.0 * xi)) * xi;
     return -0.5 * s * s;
@@ -608,7 +626,7 @@ solve(double x, double u, double& f, double& fp)
         double g = f - x;
         if (fabs(g) <= 1e-9 * x || !(fp > 1e-300)) return u;
         double den = 2.0 * fp * fp - g * fpp;
-        double du = (den > 0.0) ? 2.0 * g * fp / den : g / fp;
+        double du = (den > 0.0) ? 2.0 * g * fp * fm::rcp(den) : g * fm::rcp(fp);
         double un = u - du;
         if (un >= kUMax) un = 0.5 * (u + kUMax);  // never step onto / over the pole
         if (NEG && un > -1e-3) un = 0.5 * (u - 1e-3);
@@ -680,7 +698,7 @@ struct SaddleT {
     static constexpr int kFields = FULL ? 9 : FAR ? 4 : 6;
 
     struct Par {
-        double h, half_z2, xl, xc, slope_l, c_l, a1, a2;
+        double h, inv_h, half_z2, xl, xc, slope_l, c_l, a1, a2;
         double w_left, c_r, slope_r;  // FULL only
     };
     struct State {
@@ -766,11 +784,12 @@ struct SaddleT {
     static __device__ __forceinline__ bool load(const Rec& rec, Par& p, State& s, bool)
     {
         p.h = rec[0];
+        p.inv_h = fm::rcp(p.h);
         double zz = rec[1];
         p.half_z2 = 0.5 * zz * zz;
         p.xl = rec[2];
         p.xc = 2.75 * p.xl;
-        p.slope_l = -0.5 / (p.xl * p.xl);
+        p.slope_l = -0.5 * fm::rcp(p.xl * p.xl);
         p.c_l = rec[3];
         if (!FAR) {
             p.a1 = rec[4];
@@ -799,10 +818,10 @@ struct SaddleT {
             const double mu = p.xl, mu2 = p.xl * p.xl;
             do {  // IG(mu = xl, lambda = h) | x < xc, Michael-Schucany-Haas
                 double y = r.normal();
-                double w = mu + 0.5 * mu2 * y * y / h;
-                x = mu2 / (w + sqrt(fmax(w * w - mu2, 0.0)));
+                double w = mu + 0.5 * mu2 * y * y * p.inv_h;
+                x = mu2 * fm::rcp(w + sqrt(fmax(w * w - mu2, 0.0)));
                 if (r.uniform_co() * (mu + x) > mu) {
-                    x = mu2 / x;
+                    x = mu2 * fm::rcp(x);
                 }
             } while (x >= p.xc);
         }
@@ -814,7 +833,7 @@ struct SaddleT {
         //   log phi = h (K(u) - t x) - 1/2 log K''(u),  t = u + z^2/2,  K'(u) = x
         //   log k_l = h (slope_l x - 1/(2x)) - 3/2 log x + c_l          (x <= xc)
         //   log k_r = h slope_r x + (h - 1) log x + c_r                 (x >  xc)
-        const double rx = 1.0 / x;
+        const double rx = fm::rcp(x);
         double u, fp, cum;
         if (x <= 0.2) {
             // large-argument closed form: tanh(s)/s = x solved to < 1e-10 relative by the two-pass
@@ -825,7 +844,7 @@ struct SaddleT {
             const double sx = (1.0 - corr) * rx;         // s = sqrt(-2u)
             const double dl = 2.0 * corr * rx;            // 2 (1/x - s)
             const double e2s = e * (1.0 + dl * (1.0 + 0.5 * dl));  // e^{-2s}
-            const double inv_s2 = 1.0 / (sx * sx);
+            const double inv_s2 = fm::rcp(sx * sx);
             u = -0.5 * sx * sx;
             fp = x * x - (1.0 - x) * inv_s2;
             cum = -(sx - kLog2 + e2s * (1.0 - e2s * (0.5 - e2s * (1.0 / 3.0))));
@@ -891,7 +910,7 @@ normal_approx_sample(R& r, double h, double z)
         // reciprocal rinv = 1 / ((1 + e) a) serves the mean and the variance
         const double e = exp(-a);
         const double ope = 1.0 + e;
-        const double rinv = 1.0 / (ope * a);
+        const double rinv = fm::rcp(ope * a);
         mean = 0.5 * h * (1.0 - e) * rinv;
         if (a < 1.0) {
             const double a2 = a * a;
@@ -909,7 +928,7 @@ normal_approx_sample(R& r, double h, double z)
     // mean + N sqrt(var) with the Box-Muller radius folded into one square root
     const double u1 = r.uniform_oc();
     const double u2 = r.uniform_co();
-    return mean + sqrt(-2.0 * var * log(u1)) * cospi(2.0 * u2);
+    return mean + sqrt(-2.0 * var * log(u1)) * fm::cos2pi(u2);
 }
 
 // random_polyagamma_gamma_conv (src/pgm_random.c:79-97): 200 Marsaglia-Tsang gammas
@@ -956,7 +975,7 @@ gamma_conv_sample(GammaRng& r, double h, double z)
             g *= exp(log(r.uniform_oc()) * inv_h);
         }
         double m = k + 0.5;
-        acc += g / (pi2 * m * m + z2);
+        acc += g * fm::rcp(pi2 * m * m + z2);
     }
     return 0.5 * acc;
 }

@@ -957,6 +957,37 @@ measure_fp64_peak(double* tflops, cudaStream_t s)
     return (int)cudaGetLastError();
 }
 
+// unit-test hook for the fm:: functions (pgm_cuda_test_math)
+__global__ void
+test_math_kernel(int which, const double* __restrict__ in, size_t n, double* __restrict__ out)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double x = in[i];
+        double y, t;
+        switch (which) {
+            case 0: y = fm::rcp(x); break;
+            case 1: y = fm::sqrt(x); break;
+            case 2: y = fm::log(x); break;
+            case 3: y = fm::exp(x); break;
+            case 4: y = fm::cos2pi(x); break;
+            case 5: y = fm::rsqrt(x); break;
+            case 6: fm::sincos2pi(x, y, t); break;
+            case 7: fm::sincos2pi(x, t, y); break;
+            default: y = fm::div(1.0, x); break;
+        }
+        out[i] = y;
+    }
+}
+
+int
+launch_test_math(int which, const double* d_in, size_t n, double* d_out, cudaStream_t s)
+{
+    if (n == 0) return 0;
+    test_math_kernel<<<1184, 256, 0, s>>>(which, d_in, n, d_out);
+    count_launch(1);
+    return (int)cudaGetLastError();
+}
+
 int
 launch_check_h(const double* d_h, size_t n, int devroye, int* d_flag, cudaStream_t s)
 {

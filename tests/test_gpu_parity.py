@@ -294,6 +294,50 @@ def test_c_abi_direct_call(torch, oracle):
     assert v == oracle.fill(11, 4, 1.0, 0.0, 1)[0] or abs(v / oracle.fill(11, 4, 1.0, 0.0, 1)[0] - 1) < 1e-9
 
 
+def test_fast_math(torch):
+    """The kernels' own elementary functions (fm:: in csrc/pgm_device.cuh) against numpy's libm over
+    the argument ranges the samplers produce."""
+    from polyagamma_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+
+    def run(which, x):
+        xin = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        out = torch.empty_like(xin)
+        rc = L.pgm_cuda_test_math(which, ctypes.c_void_p(xin.data_ptr()), xin.numel(), ctypes.c_void_p(out.data_ptr()),
+                                  None)
+        assert rc == 0
+        return out.cpu().numpy()
+
+    def ulps(a, b):
+        return float(np.max(np.abs(a - b) / np.spacing(np.abs(b))))
+
+    n = 2_000_000
+    pos = np.concatenate([rng.random(n) + 1e-300, 10.0 ** rng.uniform(-300, 300, n), rng.uniform(0.5, 2.0, n),
+                          np.array([1.0, 2.0, 0.5, 2.0**-53, 1 - 2.0**-53, 1e-307, 1e307])])
+    assert ulps(run(2, pos), np.log(pos)) <= 2.0
+    assert ulps(run(0, pos), 1.0 / pos) <= 1.0
+    assert ulps(run(8, pos), 1.0 / pos) <= 1.0
+    assert ulps(run(1, pos), np.sqrt(pos)) <= 1.0
+    assert ulps(run(5, pos), 1.0 / np.sqrt(pos)) <= 4.0
+    neg = -pos
+    assert ulps(run(0, neg), 1.0 / neg) <= 1.0
+    ex = np.concatenate([rng.uniform(-706, 700, n), rng.uniform(-2, 2, n), np.array([0.0, -706.9, 699.9, 1e-300])])
+    assert ulps(run(3, ex), np.exp(ex)) <= 2.0
+    assert np.array_equal(run(3, np.array([-707.5, -1e4, -np.inf])), np.zeros(3))
+    u = np.concatenate([rng.random(n), np.array([0.0, 0.25, 0.5, 0.75, 1.0, 0.125, 1 - 2.0**-53])])
+    for which, ref in ((4, np.cos), (7, np.cos), (6, np.sin)):
+        assert float(np.max(np.abs(run(which, u) - ref(2 * np.pi * u)))) <= 1e-15
+    # special arguments fall back to libdevice semantics
+    sp = np.array([0.0, np.inf, np.nan, -1.0, 5e-324])
+    with np.errstate(all="ignore"):
+        assert np.allclose(run(2, sp), np.log(sp), rtol=1e-15, atol=0, equal_nan=True)
+        assert np.allclose(run(1, sp), np.sqrt(sp), rtol=1e-15, atol=0, equal_nan=True)
+        assert np.array_equal(run(3, np.array([np.inf, 710.0, np.nan])), np.exp(np.array([np.inf, 710.0, np.nan])),
+                              equal_nan=True)
+
+
 # ------------------------------------------------------------------------------------------
 # densities
 # ------------------------------------------------------------------------------------------
