@@ -694,6 +694,20 @@ device_info()
     return d;
 }
 
+// one helper stream per device for the overlapped bucketing pre-pass
+static cudaStream_t
+helper_stream()
+{
+    static cudaStream_t streams[64] = {};
+    static std::mutex mu;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    cudaStream_t& st = streams[dev & 63];
+    if (st == nullptr && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) st = nullptr;
+    return st;
+}
+
 static inline uint32_t
 grid_for(uint64_t full, uint64_t count_hint, uint32_t threads)
 {
@@ -822,8 +836,14 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     // (they split into specialised kernels); devroye and gamma run on the identity range.
     const bool bucketed = (m == kHybrid || m == kSaddle || m == kAlternate);
     int lg = first_chunk_log2(n);
+    // With several passes the bucketing of pass k+1 (HBM- and issue-bound) runs on a helper stream
+    // while the sampling kernels of pass k (FP64-bound) run on the caller's stream; the bucketing
+    // scratch is double-buffered, the records are not (setup and sampling are serialised on the
+    // caller's stream).
+    const bool overlap = bucketed && n > (1ull << lg) && getenv("PGM_CUDA_NO_OVERLAP") == nullptr;
+    const int nprep = overlap ? 2 : 1;
     uint64_t chunk = 0;
-    size_t list_bytes = 0, meth_bytes = 0, hist_bytes = 0, par_bytes = 0;
+    size_t list_bytes = 0, meth_bytes = 0, hist_bytes = 0, par_bytes = 0, prep_bytes = 0;
     const size_t ctl_bytes = align256(kCtlWords * sizeof(uint32_t));
     char* ws = nullptr;
     for (;;) {
@@ -835,72 +855,133 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         meth_bytes = bucketed ? align256(cmax) : 0;
         hist_bytes = bucketed ? align256((size_t)nblocks_max * kNumBuckets * sizeof(uint32_t)) : 0;
         par_bytes = (m == kGamma) ? 0 : align256(cmax * kMaxRecordFields * sizeof(double));
-        err = cudaMallocAsync(&ws, list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes + par_bytes, s);
+        prep_bytes = list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes;
+        err = cudaMallocAsync(&ws, nprep * prep_bytes + par_bytes, s);
         if (err == cudaSuccess) break;
         (void)cudaGetLastError();  // clear the sticky-free allocation error and retry smaller
         if (err != cudaErrorMemoryAllocation || lg <= kChunkLog2Min || env_chunk_log2()) return (int)err;
         --lg;
     }
-    uint32_t* list = (uint32_t*)ws;
-    uint8_t* meth = (uint8_t*)(ws + list_bytes);
-    uint32_t* block_counts = (uint32_t*)(ws + list_bytes + meth_bytes);
-    uint32_t* block_offsets = (uint32_t*)(ws + list_bytes + meth_bytes + hist_bytes);
-    uint32_t* ctl = (uint32_t*)(ws + list_bytes + meth_bytes + 2 * hist_bytes);
-    double* params = (double*)(ws + list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes);
+    struct Prep {
+        uint32_t* list;
+        uint8_t* meth;
+        uint32_t *block_counts, *block_offsets, *ctl;
+    } prep[2];
+    for (int i = 0; i < nprep; ++i) {
+        char* base = ws + (size_t)i * prep_bytes;
+        prep[i].list = (uint32_t*)base;
+        prep[i].meth = (uint8_t*)(base + list_bytes);
+        prep[i].block_counts = (uint32_t*)(base + list_bytes + meth_bytes);
+        prep[i].block_offsets = (uint32_t*)(base + list_bytes + meth_bytes + hist_bytes);
+        prep[i].ctl = (uint32_t*)(base + list_bytes + meth_bytes + 2 * hist_bytes);
+    }
+    if (nprep == 1) prep[1] = prep[0];
+    double* params = (double*)(ws + (size_t)nprep * prep_bytes);
 
     // 16-byte loads in the pre-pass need contiguous, aligned operands (a scalar operand is fine)
     const bool vec = a.bc.ndim == 0 && (a.h == nullptr || (a.h_stride == 1 && ((uintptr_t)(a.h + a.base) & 15) == 0)) &&
                      (a.z == nullptr || (a.z_stride == 1 && ((uintptr_t)(a.z + a.base) & 15) == 0));
     const uint64_t base0 = a.base;
-    for (uint64_t off = 0; off < n; off += chunk) {
-        const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
-        a.base = base0 + off;
-        cudaMemsetAsync(ctl, 0, ctl_bytes, s);
-        if (!bucketed) {
+
+    if (!bucketed) {
+        uint32_t* ctl = prep[0].ctl;
+        for (uint64_t off = 0; off < n; off += chunk) {
+            const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
+            a.base = base0 + off;
+            cudaMemsetAsync(ctl, 0, ctl_bytes, s);
             Bucket b{nullptr, nullptr, 0, cn, params, 0};
             switch (m) {
                 case kDevroye: launch_method<Devroye>(d, 0, a, b, cn, ctl + kCtlWork, s); break;
                 default: launch_dense<kGamma>(d, a, b, cn, s); break;
             }
-            continue;
         }
+        cudaFreeAsync(ws, s);
+        return (int)cudaGetLastError();
+    }
+
+    // bucketing pre-pass of one pass, on stream `sb`, into scratch set `pp`
+    auto bucketing = [&](const FillArgs& ap, uint32_t cn, const Prep& pp, cudaStream_t sb) {
         const uint32_t nblocks = (cn + kBucketTile * kTilesPerBlock - 1) / (kBucketTile * kTilesPerBlock);
+        cudaMemsetAsync(pp.ctl, 0, ctl_bytes, sb);
         {
-            ScopedKernelTimer timer(kKindClassify, s);
+            ScopedKernelTimer timer(kKindClassify, sb);
             if (vec) {
-                classify_kernel<true><<<nblocks, kBucketThreads, 0, s>>>(a, cn, m, meth, block_counts);
+                classify_kernel<true><<<nblocks, kBucketThreads, 0, sb>>>(ap, cn, m, pp.meth, pp.block_counts);
             }
             else {
-                classify_kernel<false><<<nblocks, kBucketThreads, 0, s>>>(a, cn, m, meth, block_counts);
+                classify_kernel<false><<<nblocks, kBucketThreads, 0, sb>>>(ap, cn, m, pp.meth, pp.block_counts);
             }
         }
         {
-            ScopedKernelTimer timer(kKindScan, s);
-            scan_kernel<<<1, 1024, 0, s>>>(block_counts, nblocks, block_offsets, ctl);
+            ScopedKernelTimer timer(kKindScan, sb);
+            scan_kernel<<<1, 1024, 0, sb>>>(pp.block_counts, nblocks, pp.block_offsets, pp.ctl);
         }
         {
-            ScopedKernelTimer timer(kKindScatter, s);
-            scatter_kernel<<<nblocks, kBucketThreads, 0, s>>>(meth, cn, block_offsets, ctl, list);
+            ScopedKernelTimer timer(kKindScatter, sb);
+            scatter_kernel<<<nblocks, kBucketThreads, 0, sb>>>(pp.meth, cn, pp.block_offsets, pp.ctl, pp.list);
         }
         count_launch(3);
-        // counts and list bases stay on the device: the method kernels read them there, so the
-        // host never waits for the histogram (empty buckets cost one near-empty launch)
-        auto bucket = [&](int q) { return Bucket{list, ctl, q, 0, params, 0}; };
+    };
+    // method kernels of one pass, on the caller's stream.  Counts and list bases stay on the
+    // device: the kernels read them there, so the host never waits for the histogram (empty
+    // buckets cost one near-empty launch).
+    auto sampling = [&](const FillArgs& ap, uint32_t cn, const Prep& pp) {
+        uint32_t* ctl = pp.ctl;
+        auto bucket = [&](int q) { return Bucket{pp.list, ctl, q, 0, params, 0}; };
         if (m != kAlternate) {
-            launch_method<SaddleFull>(d, 2, a, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s);
-            launch_method<SaddleLeft>(d, 3, a, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s);
-            launch_method<SaddleFar>(d, 4, a, bucket(kBSaddleFar), cn, ctl + kCtlWork + kBSaddleFar, s);
+            launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s);
+            launch_method<SaddleLeft>(d, 3, ap, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s);
+            launch_method<SaddleFar>(d, 4, ap, bucket(kBSaddleFar), cn, ctl + kCtlWork + kBSaddleFar, s);
         }
         if (m != kSaddle) {
-            launch_method<Alternate>(d, 1, a, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s);
-            launch_method<AlternateLeft>(d, 5, a, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft, s);
+            launch_method<Alternate>(d, 1, ap, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s);
+            launch_method<AlternateLeft>(d, 5, ap, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft, s);
         }
         if (m == kHybrid) {
-            launch_method<Devroye>(d, 0, a, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s);
-            launch_dense<kNormal>(d, a, bucket(kBNormal), cn, s);
+            launch_method<Devroye>(d, 0, ap, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s);
+            launch_dense<kNormal>(d, ap, bucket(kBNormal), cn, s);
         }
+    };
+
+    if (!overlap) {
+        for (uint64_t off = 0; off < n; off += chunk) {
+            const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
+            a.base = base0 + off;
+            bucketing(a, cn, prep[0], s);
+            sampling(a, cn, prep[0]);
+        }
+        cudaFreeAsync(ws, s);
+        return (int)cudaGetLastError();
+    }
+
+    cudaStream_t sb = helper_stream();
+    if (sb == nullptr) return (int)cudaErrorUnknown;
+    cudaEvent_t ev_ready, ev_prep[2], ev_used[2];
+    cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&ev_prep[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ev_used[i], cudaEventDisableTiming);
+    }
+    cudaEventRecord(ev_ready, s);  // inputs and the scratch allocation are ordered before this point
+    cudaStreamWaitEvent(sb, ev_ready, 0);
+    uint64_t k = 0;
+    for (uint64_t off = 0; off < n; off += chunk, ++k) {
+        const int buf = (int)(k & 1);
+        const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
+        a.base = base0 + off;
+        if (k >= 2) cudaStreamWaitEvent(sb, ev_used[buf], 0);  // sampling of pass k-2 is done with this set
+        bucketing(a, cn, prep[buf], sb);
+        cudaEventRecord(ev_prep[buf], sb);
+        cudaStreamWaitEvent(s, ev_prep[buf], 0);
+        sampling(a, cn, prep[buf]);
+        cudaEventRecord(ev_used[buf], s);
     }
     cudaFreeAsync(ws, s);
+    cudaEventDestroy(ev_ready);  // destruction is deferred until the events have completed
+    for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(ev_prep[i]);
+        cudaEventDestroy(ev_used[i]);
+    }
     return (int)cudaGetLastError();
 }
 
