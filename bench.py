@@ -43,13 +43,15 @@ WORKLOAD = "cfg4: fill2 hybrid, h~U[0.1,200], z~U[-50,50] (BASELINE.json configs
 # table in profiles/README.md (SURVEY 8(d)'s nominal per-method figures are kept beside them there).
 # devroye figures are from the cfg2 capture (cfg4 has no devroye elements).
 FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 596.0, "alternate_left": 383.0, "saddle": 602.0,
-                     "saddle_left": 642.0, "saddle_far": 298.0, "normal": 150.0, "gamma": 6.0e4,
+                     "saddle_left": 642.0, "saddle_far": 298.0, "saddle_mid": 298.0, "normal": 150.0, "gamma": 6.0e4,
                      "setup_devroye": 356.0, "setup_alternate": 1222.0, "setup_alternate_left": 1.0,
-                     "setup_saddle": 1790.0, "setup_saddle_left": 363.0, "setup_saddle_far": 269.0}
+                     "setup_saddle": 1790.0, "setup_saddle_left": 363.0, "setup_saddle_far": 269.0,
+                     "setup_saddle_mid": 269.0}
 KERNEL_NAMES = {"devroye": "sample_kernel<Devroye>", "alternate": "sample_kernel<Alternate>",
                 "alternate_left": "sample_kernel<AlternateLeft>", "setup_alternate_left": "setup_kernel<AlternateLeft>",
                 "saddle": "sample_kernel<SaddleFull>", "saddle_left": "sample_kernel<SaddleLeft>",
-                "saddle_far": "sample_kernel<SaddleFar>",
+                "saddle_far": "sample_kernel<SaddleFar>", "saddle_mid": "sample_kernel<SaddleFar> (8<=|z|<14)",
+                "setup_saddle_mid": "setup_kernel<SaddleFar> (8<=|z|<14)",
                 "normal": "dense_kernel<normal>", "gamma": "dense_kernel<gamma>",
                 "setup_devroye": "setup_kernel<Devroye>", "setup_alternate": "setup_kernel<Alternate>",
                 "setup_saddle": "setup_kernel<SaddleFull>", "setup_saddle_left": "setup_kernel<SaddleLeft>",
@@ -291,18 +293,19 @@ def main():
     mix = {"normal": int(normal.sum()), "saddle": int(saddle.sum()), "devroye": int(devroye.sum())}
     mix["alternate"] = n - sum(mix.values())
     left_mask = saddle & (h * (1.0 + 0.125 * z.abs()) >= 22.0)
-    saddle_far_count = int((left_mask & (z.abs() >= 8.0)).sum())
-    saddle_left_count = int(left_mask.sum()) - saddle_far_count
+    saddle_far_count = int((left_mask & (z.abs() >= 14.0)).sum())
+    saddle_mid_count = int((left_mask & (z.abs() >= 8.0)).sum()) - saddle_far_count
+    saddle_left_count = int(left_mask.sum()) - saddle_far_count - saddle_mid_count
     alt_left_count = int((~normal & ~saddle & ~devroye & (z.abs() >= 14.0)).sum())
     del left_mask
     del normal, saddle, devroye
     # saddle elements whose right envelope piece is unreachable run the left-only kernels
-    left, far = saddle_left_count, saddle_far_count
+    left, far, mid = saddle_left_count, saddle_far_count, saddle_mid_count
     units = {"devroye": mix["devroye"], "alternate": mix["alternate"] - alt_left_count,
-             "alternate_left": alt_left_count, "saddle": mix["saddle"] - left - far,
-             "saddle_left": left, "saddle_far": far, "normal": mix["normal"], "gamma": 0}
+             "alternate_left": alt_left_count, "saddle": mix["saddle"] - left - far - mid,
+             "saddle_left": left, "saddle_far": far, "saddle_mid": mid, "normal": mix["normal"], "gamma": 0}
     units.update({"setup_" + k: units[k] for k in ("devroye", "alternate", "alternate_left", "saddle", "saddle_left",
-                                                    "saddle_far")})
+                                                    "saddle_far", "saddle_mid")})
     dom = max(units, key=lambda k: kernels[k][0])
     dom_ms, dom_launches = kernels[dom]
     per_launch_s = dom_ms * 1e-3 / max(dom_launches, 1)

@@ -117,15 +117,20 @@ uint64_t pgm_cuda_launch_count(void);
  * library launches is bracketed by CUDA events on its own stream; _end synchronises those
  * events and returns, per kernel kind, the summed milliseconds and the launch count.
  * Kinds: 0 classify, 1 scan, 2 scatter; sampling kernels 3 devroye, 4 alternate, 5 saddle (both
- * envelope pieces), 6 saddle-left (left piece only, |z| < 8), 7 saddle-far (left piece, |z| >= 8),
- * 8 alternate-left (left piece only, |z| >= 14); 9 normal, 10 gamma, 11 density; per-element
- * setup kernels 12..17 in the order of 3..8.  `cap` = length of both output arrays (>= 18). */
-#define PGM_CUDA_NUM_KERNEL_KINDS 18
+ * envelope pieces), 6 saddle-left (left piece only, |z| < 8), 7 saddle-far (left piece, |z| >= 14),
+ * 8 alternate-left (left piece only, |z| >= 14), 9 saddle-mid (the far kernel on 8 <= |z| < 14);
+ * 10 normal, 11 gamma, 12 density; per-element setup kernels 13..19 in the order of 3..9.
+ * `cap` = length of both output arrays (>= 20). */
+#define PGM_CUDA_NUM_KERNEL_KINDS 20
 void pgm_cuda_profile_begin(void);
 int pgm_cuda_profile_end(double* ms, uint64_t* launches, int cap);
 /* FP64 (DFMA) peak of the current device in TFLOP/s, measured by a register-resident FMA
  * microbenchmark: the denominator of the FP64 roofline.  Synchronises `stream`. */
 int pgm_cuda_fp64_peak_tflops(double* tflops, void* stream);
+/* The per-pass scratch (up to ~80 B per element of a 2^27-element pass) is allocated stream-ordered
+ * from the device's default memory pool and stays cached there between calls.  This returns the
+ * cached blocks of the current device to the driver (synchronises the device). */
+int pgm_cuda_release_scratch(void);
 /* Unit-test hook: applies one of the kernels' own elementary functions (csrc/pgm_device.cuh, fm::)
  * elementwise.  which: 0 rcp, 1 sqrt, 2 log, 3 exp, 4 cos(2 pi x), 5 rsqrt, 6 sin(2 pi x) and
  * 7 cos(2 pi x) of the paired routine, 8 1/x by fm::div. */

@@ -5,7 +5,7 @@ Drop-in for the hot path of zoj613/polyagamma: ``random_polyagamma``, ``polyagam
 as hand-written FP64 CUDA kernels behind the C-ABI of ``include/pgm_cuda.h``.
 """
 from ._api import PhiloxGenerator, polyagamma_cdf, polyagamma_pdf, random_polyagamma
-from ._lib import ExtensionMissing, launch_count
+from ._lib import ExtensionMissing, launch_count, release_scratch
 
 __version__ = "0.1.0"
 __all__ = [
@@ -15,4 +15,5 @@ __all__ = [
     "PhiloxGenerator",
     "ExtensionMissing",
     "launch_count",
+    "release_scratch",
 ]

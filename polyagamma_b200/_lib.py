@@ -36,6 +36,7 @@ EXPORTS = (
     "pgm_cuda_profile_end",
     "pgm_cuda_fp64_peak_tflops",
     "pgm_cuda_test_math",
+    "pgm_cuda_release_scratch",
     "pgm_cuda_version",
     "pgm_cuda_hybrid_select",
     "pgm_cuda_call_key",
@@ -88,6 +89,8 @@ def lib() -> ctypes.CDLL:
     L.pgm_cuda_profile_end.argtypes = [ctypes.POINTER(d), ctypes.POINTER(u64), i]
     L.pgm_cuda_fp64_peak_tflops.restype = i
     L.pgm_cuda_fp64_peak_tflops.argtypes = [ctypes.POINTER(d), vp]
+    L.pgm_cuda_release_scratch.restype = i
+    L.pgm_cuda_release_scratch.argtypes = []
     L.pgm_cuda_test_math.restype = i
     L.pgm_cuda_test_math.argtypes = [i, vp, sz, vp, vp]
     L.pgm_cuda_version.restype = ctypes.c_char_p
@@ -113,11 +116,16 @@ def int64_array(values):
     return arr
 
 
+def release_scratch() -> None:
+    """Return the library's cached per-pass scratch of the current device to the driver."""
+    check(lib().pgm_cuda_release_scratch(), "pgm_cuda_release_scratch")
+
+
 def launch_count() -> int:
     return int(lib().pgm_cuda_launch_count())
 
 
-_METHOD_KERNELS = ("devroye", "alternate", "saddle", "saddle_left", "saddle_far", "alternate_left")
+_METHOD_KERNELS = ("devroye", "alternate", "saddle", "saddle_left", "saddle_far", "alternate_left", "saddle_mid")
 KERNEL_KINDS = (("classify", "scan", "scatter") + _METHOD_KERNELS + ("normal", "gamma", "density") +
                 tuple("setup_" + k for k in _METHOD_KERNELS))
 

@@ -128,6 +128,18 @@ pgm_cuda_fp64_peak_tflops(double* tflops, void* stream)
 }
 
 int
+pgm_cuda_release_scratch(void)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaMemPool_t pool;
+    if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;
+    return (int)cudaMemPoolTrimTo(pool, 0);
+}
+
+int
 pgm_cuda_test_math(int which, const double* d_in, size_t n, double* d_out, void* stream)
 {
     if (n != 0 && (d_in == nullptr || d_out == nullptr)) return PGM_CUDA_EINVAL;

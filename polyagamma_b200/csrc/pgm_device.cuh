@@ -136,7 +136,7 @@ rsqrt(double x)
 __device__ __forceinline__ double
 sqrt(double x)
 {
-    if (!(x > 2.3e-308)) return ::sqrt(x);  // zero, denormal, negative, NaN
+    if (!(x > 2.3e-308 && x < 1.7e308)) return ::sqrt(x);  // zero, denormal, negative, NaN, inf
     const double y = rsqrt(x);
     const double s = x * y;
     return fma(fma(-s, s, x), 0.5 * y, s);

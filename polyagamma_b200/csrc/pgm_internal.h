@@ -58,13 +58,14 @@ enum : int {
     kKindClassify = 0,
     kKindScan = 1,
     kKindScatter = 2,
-    // sampling kernels: + 0 devroye, 1 alternate, 2 saddle, 3 saddle-left, 4 saddle-far, 5 alternate-left
+    // sampling kernels: + 0 devroye, 1 alternate, 2 saddle, 3 saddle-left, 4 saddle-far, 5 alternate-left,
+    // 6 saddle-mid
     kKindDevroye = 3,
-    kKindNormal = 9,
-    kKindGamma = 10,
-    kKindDensity = 11,
-    kKindSetup = 12,  // setup kernels, same order as the sampling kernels
-    kNumKinds = 18
+    kKindNormal = 10,
+    kKindGamma = 11,
+    kKindDensity = 12,
+    kKindSetup = 13,  // setup kernels, same order as the sampling kernels
+    kNumKinds = 20
 };
 
 class ScopedKernelTimer {

@@ -934,48 +934,46 @@ normal_approx_sample(R& r, double h, double z)
 // random_polyagamma_gamma_conv (src/pgm_random.c:79-97): 200 Marsaglia-Tsang gammas
 using GammaRng = RngFor<6>;
 
+// random_polyagamma_gamma_conv (src/pgm_random.c:79-97): 1/2 sum_{k<200} Gamma(h, 1) / (pi^2 (k+1/2)^2 + z^2/4)
+// with Marsaglia-Tsang gammas (shape < 1: Gamma(h + 1) U^{1/h}).  One trip of the loop draws ONE
+// Box-Muller pair and makes TWO Marsaglia-Tsang attempts with it, so all lanes of a warp stay in
+// phase (a "spare normal" flag drifts apart between lanes after the first rejection and halves the
+// active lanes); the draw order is exactly that of the oracle's spare-normal loop.
 __device__ inline double
 gamma_conv_sample(GammaRng& r, double h, double z)
 {
     double zz = 0.5 * fabs(z);
     if (!(zz > 0.0)) zz = 0.0;
     const double pi2 = 9.869604401089358;
-    double z2 = zz * zz;
-    bool boost = h < 1.0;
-    double d = (boost ? h + 1.0 : h) - 1.0 / 3.0;
-    double c = 1.0 / sqrt(9.0 * d);
-    double inv_h = 1.0 / h;
+    const double z2 = zz * zz;
+    const bool boost = h < 1.0;
+    const double d = (boost ? h + 1.0 : h) - 1.0 / 3.0;
+    const double c = fm::rsqrt(9.0 * d);
+    const double inv_h = fm::rcp(h);
     double acc = 0.0;
-    bool has_spare = false;
-    double spare = 0.0;
-    for (int k = 0; k < 200; ++k) {
-        double g;
-        for (;;) {
-            double x, v;
-            do {
-                if (has_spare) {
-                    x = spare;
-                    has_spare = false;
+    int k = 0;
+    while (k < 200) {
+        double nrm[2];
+        r.normal_pair(nrm[0], nrm[1]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (k < 200) {
+                const double x = nrm[j];
+                double v = 1.0 + c * x;
+                if (v > 0.0) {
+                    v = v * v * v;
+                    const double u = r.uniform_oc();
+                    const double x2 = x * x;
+                    if (u < 1.0 - 0.0331 * x2 * x2 || log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) {
+                        double g = d * v;
+                        if (boost) g *= exp(log(r.uniform_oc()) * inv_h);
+                        const double m = k + 0.5;
+                        acc += g * fm::rcp(pi2 * m * m + z2);
+                        ++k;
+                    }
                 }
-                else {
-                    r.normal_pair(x, spare);
-                    has_spare = true;
-                }
-                v = 1.0 + c * x;
-            } while (v <= 0.0);
-            v = v * v * v;
-            double u = r.uniform_oc();
-            double x2 = x * x;
-            if (u < 1.0 - 0.0331 * x2 * x2 || log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) {
-                g = d * v;
-                break;
             }
         }
-        if (boost) {
-            g *= exp(log(r.uniform_oc()) * inv_h);
-        }
-        double m = k + 0.5;
-        acc += g * fm::rcp(pi2 * m * m + z2);
     }
     return 0.5 * acc;
 }

@@ -146,8 +146,9 @@ constexpr int kBucketTile = kBucketThreads * kBucketItems;  // elements per bloc
 constexpr uint8_t kBucketNone = 255;
 
 // bucket ids (also the order of the per-method lists inside the chunk's index list)
+// (the gamma method never needs the pre-pass: it runs on the identity range)
 enum : int { kBDevroye = 0, kBAlternate = 1, kBSaddleFull = 2, kBSaddleLeft = 3, kBSaddleFar = 4, kBAlternateLeft = 5,
-             kBNormal = 6, kBGamma = 7, kNumBuckets = 8 };
+             kBSaddleMid = 6, kBNormal = 7, kNumBuckets = 8, kBGamma = 8 };
 
 // ctl layout (uint32): [0..7] bucket counts, [8..15] list bases, [16..23] work counters
 constexpr int kCtlCount = 0, kCtlBase = 8, kCtlWork = 16, kCtlWords = 32;
@@ -159,8 +160,11 @@ bucket_of(int method, double h, double z, bool compat)
         case kDevroye: return kBDevroye;
         case kAlternate: return alternate_left_only(z) ? kBAlternateLeft : kBAlternate;
         case kSaddle: {
+            // the far kernel's buckets: |z| >= 14 (proposals below x = 0.2 almost surely: closed-form
+            // solve for every lane) and 8 <= |z| < 14 (a mix of closed-form and iterative solves)
             int sm = saddle_mode(h, z, compat);
-            return sm == kSaddleFull ? kBSaddleFull : sm == kSaddleLeft ? kBSaddleLeft : kBSaddleFar;
+            return sm == kSaddleFull ? kBSaddleFull : sm == kSaddleLeft ? kBSaddleLeft
+                   : fabs(z) >= 14.0 ? kBSaddleFar : kBSaddleMid;
         }
         case kNormal: return kBNormal;
         default: return kBGamma;
@@ -657,8 +661,9 @@ check_h_kernel(const double* __restrict__ h, size_t n, int devroye, int* __restr
 // ---------------------------------------------------------------------------------------
 struct DeviceInfo {
     int sms = 0;
-    // sampling kernels: devroye, alternate, saddle-full, saddle-left, saddle-far, alternate-left
-    int blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};
+    // sampling kernels: devroye, alternate, saddle-full, saddle-left, saddle-far, alternate-left,
+    // saddle-mid (the far kernel on its second bucket)
+    int blocks_per_sm[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 static DeviceInfo
@@ -676,7 +681,8 @@ device_info()
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[3], sample_kernel<SaddleLeft>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[4], sample_kernel<SaddleFar>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[5], sample_kernel<AlternateLeft>, kPersistThreads, 0);
-        for (int i = 0; i < 6; ++i) {
+        d.blocks_per_sm[6] = d.blocks_per_sm[4];
+        for (int i = 0; i < 7; ++i) {
             if (d.blocks_per_sm[i] < 1) d.blocks_per_sm[i] = 1;
         }
         // starting-point tables of the saddle setup (per device, filled by the solver itself)
@@ -717,7 +723,7 @@ grid_for(uint64_t full, uint64_t count_hint, uint32_t threads)
 }
 
 // setup + persistent sampling of one bucket with method M (which: 0 devroye, 1 alternate,
-// 2 saddle-full, 3 saddle-left, 4 saddle-far, 5 alternate-left; profiling kinds are
+// 2 saddle-full, 3 saddle-left, 4 saddle-far, 5 alternate-left, 6 saddle-mid; profiling kinds are
 // kKindDevroye / kKindSetup + which)
 template <class M>
 static void
@@ -824,6 +830,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
                 case kBSaddleLeft: launch_method<SaddleLeft>(d, 3, a, b, cn, counters + c, s); break;
                 case kBSaddleFar: launch_method<SaddleFar>(d, 4, a, b, cn, counters + c, s); break;
                 case kBAlternateLeft: launch_method<AlternateLeft>(d, 5, a, b, cn, counters + c, s); break;
+                case kBSaddleMid: launch_method<SaddleFar>(d, 6, a, b, cn, counters + c, s); break;
                 case kBNormal: launch_dense<kNormal>(d, a, b, cn, s); break;
                 default: launch_dense<kGamma>(d, a, b, cn, s); break;
             }
@@ -932,6 +939,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
             launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s);
             launch_method<SaddleLeft>(d, 3, ap, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s);
             launch_method<SaddleFar>(d, 4, ap, bucket(kBSaddleFar), cn, ctl + kCtlWork + kBSaddleFar, s);
+            launch_method<SaddleFar>(d, 6, ap, bucket(kBSaddleMid), cn, ctl + kCtlWork + kBSaddleMid, s);
         }
         if (m != kSaddle) {
             launch_method<Alternate>(d, 1, ap, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s);

@@ -188,6 +188,8 @@ def test_return_types_and_out_semantics(pg):
     assert torch.allclose(dout32.double(), res, rtol=1e-6)
     with pytest.raises(ValueError, match="`h` must be positive"):
         pg.random_polyagamma(torch.tensor([1.0, -2.0], device="cuda", dtype=torch.float64))
+    pg.release_scratch()  # cached pass scratch goes back to the driver; the next call re-allocates
+    assert pg.random_polyagamma(h, 1.0, random_state=(1, 1)).equal(res)
     g = pg.PhiloxGenerator(11)
     a = pg.random_polyagamma(size=4, random_state=g)
     b = pg.random_polyagamma(size=4, random_state=g)
