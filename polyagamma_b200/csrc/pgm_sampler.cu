@@ -700,16 +700,17 @@ device_info()
     return d;
 }
 
-// one helper stream per device for the overlapped bucketing pre-pass
+// helper streams per device: 0 for the overlapped bucketing pre-pass, 1 and 2 for the small
+// buckets' kernels (they run beside the big buckets' kernels and fill their tails)
 static cudaStream_t
-helper_stream()
+helper_stream(int which)
 {
-    static cudaStream_t streams[64] = {};
+    static cudaStream_t streams[64][3] = {};
     static std::mutex mu;
     int dev = 0;
     cudaGetDevice(&dev);
     std::lock_guard<std::mutex> lock(mu);
-    cudaStream_t& st = streams[dev & 63];
+    cudaStream_t& st = streams[dev & 63][which];
     if (st == nullptr && cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) st = nullptr;
     return st;
 }
@@ -884,6 +885,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     }
     if (nprep == 1) prep[1] = prep[0];
     double* params = (double*)(ws + (size_t)nprep * prep_bytes);
+    const uint64_t cmax_elems = n < chunk ? n : chunk;
 
     // 16-byte loads in the pre-pass need contiguous, aligned operands (a scalar operand is fine)
     const bool vec = a.bc.ndim == 0 && (a.h == nullptr || (a.h_stride == 1 && ((uintptr_t)(a.h + a.base) & 15) == 0)) &&
@@ -932,64 +934,86 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     // method kernels of one pass, on the caller's stream.  Counts and list bases stay on the
     // device: the kernels read them there, so the host never waits for the histogram (empty
     // buckets cost one near-empty launch).
-    auto sampling = [&](const FillArgs& ap, uint32_t cn, const Prep& pp) {
+    // The buckets of a pass are independent (disjoint elements, disjoint record regions), so the
+    // small ones run on two helper streams beside the big ones: their kernels, which are mostly
+    // launch tail, fill the tails of the others.  s1/s2 == s serialises everything on `s`.
+    auto sampling = [&](const FillArgs& ap, uint32_t cn, const Prep& pp, cudaStream_t s1, cudaStream_t s2) {
         uint32_t* ctl = pp.ctl;
         auto bucket = [&](int q) { return Bucket{pp.list, ctl, q, 0, params, 0}; };
         if (m != kAlternate) {
-            launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s);
-            launch_method<SaddleLeft>(d, 3, ap, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s);
             launch_method<SaddleFar>(d, 4, ap, bucket(kBSaddleFar), cn, ctl + kCtlWork + kBSaddleFar, s);
-            launch_method<SaddleFar>(d, 6, ap, bucket(kBSaddleMid), cn, ctl + kCtlWork + kBSaddleMid, s);
+            launch_method<SaddleFar>(d, 6, ap, bucket(kBSaddleMid), cn, ctl + kCtlWork + kBSaddleMid, s1);
+            launch_method<SaddleLeft>(d, 3, ap, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s1);
+            launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s2);
         }
         if (m != kSaddle) {
-            launch_method<Alternate>(d, 1, ap, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s);
-            launch_method<AlternateLeft>(d, 5, ap, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft, s);
+            launch_method<Alternate>(d, 1, ap, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s2);
+            launch_method<AlternateLeft>(d, 5, ap, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft,
+                                         m == kAlternate ? s : s1);
         }
         if (m == kHybrid) {
-            launch_method<Devroye>(d, 0, ap, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s);
+            launch_method<Devroye>(d, 0, ap, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s2);
             launch_dense<kNormal>(d, ap, bucket(kBNormal), cn, s);
         }
     };
 
-    if (!overlap) {
+    const bool multi = cmax_elems >= (1ull << 20) && getenv("PGM_CUDA_NO_OVERLAP") == nullptr;
+    if (!overlap && !multi) {
         for (uint64_t off = 0; off < n; off += chunk) {
             const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
             a.base = base0 + off;
             bucketing(a, cn, prep[0], s);
-            sampling(a, cn, prep[0]);
+            sampling(a, cn, prep[0], s, s);
         }
         cudaFreeAsync(ws, s);
         return (int)cudaGetLastError();
     }
 
-    cudaStream_t sb = helper_stream();
-    if (sb == nullptr) return (int)cudaErrorUnknown;
-    cudaEvent_t ev_ready, ev_prep[2], ev_used[2];
-    cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming);
-    for (int i = 0; i < 2; ++i) {
-        cudaEventCreateWithFlags(&ev_prep[i], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&ev_used[i], cudaEventDisableTiming);
+    // (the caller's stream `s` may be the null handle of the default stream: compare helpers only)
+    cudaStream_t hb = overlap ? helper_stream(0) : nullptr;
+    cudaStream_t h1 = multi ? helper_stream(1) : nullptr, h2 = multi ? helper_stream(2) : nullptr;
+    if ((overlap && hb == nullptr) || (multi && (h1 == nullptr || h2 == nullptr))) {
+        cudaFreeAsync(ws, s);
+        return (int)cudaErrorUnknown;
     }
+    cudaStream_t sb = overlap ? hb : s;
+    cudaStream_t s1 = multi ? h1 : s, s2 = multi ? h2 : s;
+    cudaEvent_t ev[8];  // 0 ready, 1-2 prep[buf], 3-4 used[buf], 5 go, 6-7 helper streams done
+    for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEvent_t ev_ready = ev[0], *ev_prep = ev + 1, *ev_used = ev + 3, ev_go = ev[5], *ev_done = ev + 6;
     cudaEventRecord(ev_ready, s);  // inputs and the scratch allocation are ordered before this point
-    cudaStreamWaitEvent(sb, ev_ready, 0);
+    if (overlap) cudaStreamWaitEvent(sb, ev_ready, 0);
     uint64_t k = 0;
     for (uint64_t off = 0; off < n; off += chunk, ++k) {
-        const int buf = (int)(k & 1);
+        const int buf = overlap ? (int)(k & 1) : 0;
         const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
         a.base = base0 + off;
-        if (k >= 2) cudaStreamWaitEvent(sb, ev_used[buf], 0);  // sampling of pass k-2 is done with this set
-        bucketing(a, cn, prep[buf], sb);
-        cudaEventRecord(ev_prep[buf], sb);
-        cudaStreamWaitEvent(s, ev_prep[buf], 0);
-        sampling(a, cn, prep[buf]);
-        cudaEventRecord(ev_used[buf], s);
+        if (overlap) {
+            if (k >= 2) cudaStreamWaitEvent(sb, ev_used[buf], 0);  // pass k-2 is done with this scratch set
+            bucketing(a, cn, prep[buf], sb);
+            cudaEventRecord(ev_prep[buf], sb);
+            cudaStreamWaitEvent(s, ev_prep[buf], 0);
+        }
+        else {
+            bucketing(a, cn, prep[buf], s);
+        }
+        if (multi) {
+            // `s` is past the previous pass (it joined the helpers there) and past this pass's bucketing
+            cudaEventRecord(ev_go, s);
+            cudaStreamWaitEvent(s1, ev_go, 0);
+            cudaStreamWaitEvent(s2, ev_go, 0);
+        }
+        sampling(a, cn, prep[buf], s1, s2);
+        if (multi) {
+            cudaEventRecord(ev_done[0], s1);
+            cudaEventRecord(ev_done[1], s2);
+            cudaStreamWaitEvent(s, ev_done[0], 0);
+            cudaStreamWaitEvent(s, ev_done[1], 0);
+        }
+        if (overlap) cudaEventRecord(ev_used[buf], s);
     }
     cudaFreeAsync(ws, s);
-    cudaEventDestroy(ev_ready);  // destruction is deferred until the events have completed
-    for (int i = 0; i < 2; ++i) {
-        cudaEventDestroy(ev_prep[i]);
-        cudaEventDestroy(ev_used[i]);
-    }
+    for (auto& e : ev) cudaEventDestroy(e);  // destruction is deferred until the events have completed
     return (int)cudaGetLastError();
 }
 
