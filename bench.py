@@ -47,6 +47,13 @@ FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 596.0, "alternate_left": 383
                      "setup_devroye": 356.0, "setup_alternate": 1222.0, "setup_alternate_left": 1.0,
                      "setup_saddle": 1790.0, "setup_saddle_left": 363.0, "setup_saddle_far": 269.0,
                      "setup_saddle_mid": 269.0}
+# DRAM bytes per element of each kernel: (dram__bytes_read.sum + dram__bytes_write.sum) of the same ncu
+# capture divided by the elements of that launch.  Algorithmic bytes are 28 (normal: list index + h + z +
+# out) to ~90 (record kernels); the sparse buckets pay 32-byte sectors for 8-byte gathers of h and z.
+DRAM_BYTES_PER_ELEMENT = {"normal": 42.1, "saddle_far": 82.0, "saddle_mid": 82.0, "saddle_left": 107.4,
+                          "saddle": 118.1, "alternate": 80.1, "alternate_left": 69.5, "setup_saddle_far": 116.9,
+                          "setup_saddle_mid": 116.9, "setup_saddle_left": 241.9, "setup_saddle": 259.2,
+                          "setup_alternate": 257.2, "setup_alternate_left": 231.8}
 KERNEL_NAMES = {"devroye": "sample_kernel<Devroye>", "alternate": "sample_kernel<Alternate>",
                 "alternate_left": "sample_kernel<AlternateLeft>", "setup_alternate_left": "setup_kernel<AlternateLeft>",
                 "saddle": "sample_kernel<SaddleFull>", "saddle_left": "sample_kernel<SaddleLeft>",
@@ -278,9 +285,21 @@ def main():
     torch.cuda.synchronize()
     barrier()
     elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
-    kernels = _lib.profile_end()
+    kernels_overlapped = _lib.profile_end()
     launches = pg.launch_count() - launches0
     clock_info = clocks.stop()
+    # In the timed region the kernels of a pass run concurrently (helper streams), so a kernel's
+    # event-bracketed time includes the others' share of the SMs.  Per-kernel roofline numbers
+    # come from the same K steps run once more with the kernels serialised on one stream.
+    os.environ["PGM_CUDA_NO_OVERLAP"] = "1"
+    step(0)
+    torch.cuda.synchronize()
+    _lib.profile_begin()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    torch.cuda.synchronize()
+    kernels = _lib.profile_end()
+    del os.environ["PGM_CUDA_NO_OVERLAP"]
     value = world * n * args.steps / (elapsed_ms * 1e-3)
     finite = bool(torch.isfinite(out[:: max(1, n // 1_000_000)]).all())
 
@@ -312,13 +331,22 @@ def main():
     units_per_launch = units[dom] * args.steps / max(dom_launches, 1)
     achieved = units_per_launch * FLOPS_PER_ELEMENT[dom] / per_launch_s / 1e12
     total_kernel_ms = sum(v[0] for v in kernels.values())
+    step_flops = sum(units[k] * FLOPS_PER_ELEMENT[k] for k in units)
+    aggregate_tflops = step_flops * args.steps / (elapsed_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp64", "kernel": KERNEL_NAMES[dom],
         "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
         "peak_source": "DFMA microbenchmark (pgm_cuda_fp64_peak_tflops) run in this process",
         "flops_per_unit": FLOPS_PER_ELEMENT[dom], "units_per_launch": units_per_launch,
         "launch_ms": per_launch_s * 1e3, "share_of_step": dom_ms / total_kernel_ms if total_kernel_ms else None,
-        "traffic": None,
+        "traffic": (units_per_launch * DRAM_BYTES_PER_ELEMENT[dom]) if dom in DRAM_BYTES_PER_ELEMENT else None,
+        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per element (profiles/r1g_cfg4_all_kernels.txt) "
+                          "x elements of this launch",
+        "timing": "per-kernel times: same K steps with the kernels serialised (PGM_CUDA_NO_OVERLAP=1); the timed "
+                  "region itself overlaps the kernels of a pass on helper streams",
+        "whole_step": {"fp64_flops_per_step": step_flops, "tflops": aggregate_tflops,
+                       "frac": aggregate_tflops / fp64_peak,
+                       "note": "all kernels' executed FP64 flops / timed step, against the same DFMA peak"},
         "hbm": {"achieved_gbs": n * args.steps * BYTES_PER_ELEMENT / (elapsed_ms * 1e-3) / 1e9,
                 "peak_gbs": hbm_peak, "frac": n * args.steps * BYTES_PER_ELEMENT / (elapsed_ms * 1e-3) / 1e9 / hbm_peak,
                 "bytes_per_unit": BYTES_PER_ELEMENT, "peak_source": peaks_src},
@@ -327,6 +355,7 @@ def main():
                            "frac": units[k] * args.steps * FLOPS_PER_ELEMENT[k] / (kernels[k][0] * 1e-3) / 1e12 / fp64_peak}
                        for k in units if kernels[k][1] and kernels[k][0] > 0 and units[k] > 0},
         "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kernels.items() if v[1]},
+        "kernel_ms_per_step_overlapped": {k: v[0] / args.steps for k, v in kernels_overlapped.items() if v[1]},
         "kernel_launches": {k: v[1] for k, v in kernels.items() if v[1]},
     }
 
