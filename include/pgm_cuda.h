@@ -110,6 +110,19 @@ int pgm_cuda_polyagamma_density_strided(int which, const double* d_x, const doub
                                         const int64_t* x_strides, const int64_t* h_strides,
                                         const int64_t* z_strides, double* d_out, void* stream);
 
+/* ---- next row of the path: the logistic-regression Gibbs omega-step ---------- */
+/* The caller pattern of the batched fill (README.md:146-148; Polson, Scott & Windle 2013):
+ *     psi = X beta;   omega_i ~ PG(n_i, psi_i);   G = X^T diag(omega) X
+ * X: n x p row-major FP64 with leading dimension ldx (in doubles), 1 <= p <= 64; beta: p;
+ * d_ntrials: n shape parameters, or NULL to use `ntrials_scalar` for every row; d_gram: p x p
+ * row-major, overwritten (deterministic reduction order); d_omega / d_psi: n doubles each, or NULL
+ * if the caller does not need them.  omega is exactly what pgm_cuda_random_polyagamma_fill2 draws
+ * for (n_trials, psi) with the same (seed, offset, first_index). */
+int pgm_cuda_logistic_omega_step(uint64_t seed, uint64_t offset, const double* d_X, size_t n, int p, size_t ldx,
+                                 const double* d_beta, const double* d_ntrials, double ntrials_scalar,
+                                 int method, double* d_gram, double* d_omega, double* d_psi,
+                                 uint64_t first_index, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------- */
 /* Number of kernels this library has launched in this process (all threads). */
 uint64_t pgm_cuda_launch_count(void);
@@ -119,9 +132,9 @@ uint64_t pgm_cuda_launch_count(void);
  * Kinds: 0 classify, 1 scan, 2 scatter; sampling kernels 3 devroye, 4 alternate, 5 saddle (both
  * envelope pieces), 6 saddle-left (left piece only, |z| < 8), 7 saddle-far (left piece, |z| >= 14),
  * 8 alternate-left (left piece only, |z| >= 14), 9 saddle-mid (the far kernel on 8 <= |z| < 14);
- * 10 normal, 11 gamma, 12 density; per-element setup kernels 13..19 in the order of 3..9.
- * `cap` = length of both output arrays (>= 20). */
-#define PGM_CUDA_NUM_KERNEL_KINDS 20
+ * 10 normal, 11 gamma, 12 density; per-element setup kernels 13..19 in the order of 3..9;
+ * 20 psi = X beta, 21 weighted Gram matrix.  `cap` = length of both output arrays (>= 22). */
+#define PGM_CUDA_NUM_KERNEL_KINDS 22
 void pgm_cuda_profile_begin(void);
 int pgm_cuda_profile_end(double* ms, uint64_t* launches, int cap);
 /* FP64 (DFMA) peak of the current device in TFLOP/s, measured by a register-resident FMA

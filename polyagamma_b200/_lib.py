@@ -31,6 +31,7 @@ EXPORTS = (
     "pgm_cuda_polyagamma_logpdf",
     "pgm_cuda_polyagamma_logcdf",
     "pgm_cuda_polyagamma_density_strided",
+    "pgm_cuda_logistic_omega_step",
     "pgm_cuda_launch_count",
     "pgm_cuda_profile_begin",
     "pgm_cuda_profile_end",
@@ -81,6 +82,8 @@ def lib() -> ctypes.CDLL:
         f.argtypes = [vp, vp, vp, sz, vp, vp]
     L.pgm_cuda_polyagamma_density_strided.restype = i
     L.pgm_cuda_polyagamma_density_strided.argtypes = [i, vp, vp, vp, i, p64, p64, p64, p64, vp, vp]
+    L.pgm_cuda_logistic_omega_step.restype = i
+    L.pgm_cuda_logistic_omega_step.argtypes = [u64, u64, vp, sz, i, sz, vp, vp, d, i, vp, vp, vp, u64, vp]
     L.pgm_cuda_launch_count.restype = u64
     L.pgm_cuda_launch_count.argtypes = []
     L.pgm_cuda_profile_begin.restype = None
@@ -127,7 +130,7 @@ def launch_count() -> int:
 
 _METHOD_KERNELS = ("devroye", "alternate", "saddle", "saddle_left", "saddle_far", "alternate_left", "saddle_mid")
 KERNEL_KINDS = (("classify", "scan", "scatter") + _METHOD_KERNELS + ("normal", "gamma", "density") +
-                tuple("setup_" + k for k in _METHOD_KERNELS))
+                tuple("setup_" + k for k in _METHOD_KERNELS) + ("gibbs_xbeta", "gibbs_gram"))
 
 
 def profile_begin() -> None:

@@ -23,6 +23,7 @@ using pgm::launch_check_h;
 using pgm::launch_count;
 using pgm::launch_density;
 using pgm::launch_fill;
+using pgm::launch_logistic_omega_step;
 using pgm::launch_test_math;
 using pgm::measure_fp64_peak;
 using pgm::profile_begin;
@@ -125,6 +126,16 @@ pgm_cuda_fp64_peak_tflops(double* tflops, void* stream)
 {
     if (tflops == nullptr) return PGM_CUDA_EINVAL;
     return measure_fp64_peak(tflops, (cudaStream_t)stream);
+}
+
+int
+pgm_cuda_logistic_omega_step(uint64_t seed, uint64_t offset, const double* d_X, size_t n, int p, size_t ldx,
+                             const double* d_beta, const double* d_ntrials, double ntrials_scalar, int method,
+                             double* d_gram, double* d_omega, double* d_psi, uint64_t first_index, void* stream)
+{
+    if (d_gram == nullptr || d_beta == nullptr || (n != 0 && d_X == nullptr)) return PGM_CUDA_EINVAL;
+    return launch_logistic_omega_step(seed, offset, d_X, n, p, ldx, d_beta, d_ntrials, ntrials_scalar, method, d_gram,
+                                      d_omega, d_psi, first_index, (cudaStream_t)stream);
 }
 
 int

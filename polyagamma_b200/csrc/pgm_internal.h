@@ -48,6 +48,9 @@ struct DensityArgs {
 int launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s);
 int launch_check_h(const double* d_h, size_t n, int devroye, int* d_flag, cudaStream_t s);
 int launch_density(int which, DensityArgs a, uint64_t n, cudaStream_t s);
+int launch_logistic_omega_step(uint64_t seed, uint64_t offset, const double* d_X, size_t n, int p, size_t ldx,
+                               const double* d_beta, const double* d_ntrials, double ntrials_scalar, int method,
+                               double* d_gram, double* d_omega, double* d_psi, uint64_t first_index, cudaStream_t s);
 uint64_t launch_count();
 void count_launch(uint64_t n);
 int measure_fp64_peak(double* tflops, cudaStream_t s);
@@ -65,7 +68,8 @@ enum : int {
     kKindGamma = 11,
     kKindDensity = 12,
     kKindSetup = 13,  // setup kernels, same order as the sampling kernels
-    kNumKinds = 20
+    kKindGibbs = 20,  // + 0 psi = X beta, 1 weighted Gram matrix
+    kNumKinds = 22
 };
 
 class ScopedKernelTimer {

@@ -1,0 +1,80 @@
+"""GPU (-m gpu): the logistic-regression Gibbs omega-step against numpy + the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+
+    return torch
+
+
+@pytest.mark.parametrize("n,p", [(1, 1), (257, 3), (1_001, 5), (10_000, 8), (7_777, 12), (20_001, 17),
+                                 (30_000, 32), (9_999, 33), (12_345, 47), (5_000, 64)])
+def test_omega_step_matches_numpy_and_oracle(torch, oracle, n, p):
+    from polyagamma_b200.gibbs import logistic_omega_step
+
+    rng = np.random.default_rng(n + p)
+    X = rng.normal(size=(n, p))
+    beta = rng.normal(scale=0.7, size=p)
+    nt = rng.integers(1, 6, n).astype(float)
+    G, omega, psi = logistic_omega_step(torch.from_numpy(X).cuda(), torch.from_numpy(beta).cuda(),
+                                        torch.from_numpy(nt).cuda(), random_state=(2024, 3), return_psi=True)
+    psi_ref = X @ beta
+    assert np.allclose(psi.cpu().numpy(), psi_ref, rtol=1e-13, atol=1e-13)
+    # the draw is the library's own fill2 on (n_trials, psi): element for element against the oracle
+    want = oracle.fill2(2024, 3, nt, psi.cpu().numpy())
+    got = omega.cpu().numpy()
+    agree = np.abs(got - want) <= 1e-9 * np.abs(want)
+    assert agree.mean() >= 1 - 1e-3
+    G_ref = X.T @ (got[:, None] * X)
+    assert np.allclose(G.cpu().numpy(), G_ref, rtol=1e-11, atol=1e-11 * np.abs(G_ref).max())
+    Gn = G.cpu().numpy()
+    assert np.array_equal(Gn, Gn.T)  # only the upper triangle is computed, then mirrored
+
+
+@pytest.mark.parametrize("p,pad", [(6, 0), (7, 1), (20, 1), (40, 0), (40, 3), (56, 2), (64, 1)])
+def test_gram_variants(torch, p, pad):
+    """Both staging granularities (16-byte copies need an even leading dimension and a 16-byte aligned
+    base) for every column-block count, against numpy."""
+    from polyagamma_b200.gibbs import logistic_omega_step
+
+    n = 40_001
+    rng = np.random.default_rng(p * 7 + pad)
+    wide = torch.from_numpy(rng.normal(size=(n, p + pad))).cuda()
+    X = wide[:, :p]
+    beta = torch.from_numpy(rng.normal(scale=0.3, size=p)).cuda()
+    G, omega = logistic_omega_step(X, beta, 2.0, random_state=(1, 2))
+    Xn, w = X.cpu().numpy(), omega.cpu().numpy()
+    G_ref = Xn.T @ (w[:, None] * Xn)
+    Gn = G.cpu().numpy()
+    assert np.allclose(Gn, G_ref, rtol=1e-11, atol=1e-11 * np.abs(G_ref).max())
+    assert np.array_equal(Gn, Gn.T)
+
+
+def test_omega_step_equals_random_polyagamma(torch):
+    """Same (seed, offset): omega is bit-identical to random_polyagamma(n_trials, psi), scalar n_trials
+    included, and the Gram matrix is reproducible run to run (fixed reduction order)."""
+    import polyagamma_b200 as pg
+    from polyagamma_b200.gibbs import logistic_omega_step
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    n, p = 1_000_003, 24
+    X = torch.randn(n, p, device="cuda", dtype=torch.float64, generator=g)
+    beta = torch.randn(p, device="cuda", dtype=torch.float64, generator=g) * 0.5
+    G1, om1, psi = logistic_omega_step(X, beta, 1.0, random_state=(9, 9), return_psi=True)
+    om2 = pg.random_polyagamma(1.0, psi, random_state=(9, 9), disable_checks=True)
+    assert torch.equal(om1, om2)
+    G2, _ = logistic_omega_step(X, beta, 1.0, random_state=(9, 9), return_omega=False)
+    assert torch.equal(G1, G2)
+    # a strided view of a wider matrix works through ldx
+    wide = torch.randn(n, p + 5, device="cuda", dtype=torch.float64, generator=g)
+    G3, om3 = logistic_omega_step(wide[:, :p], beta, 1.0, random_state=(9, 9))
+    G4, om4 = logistic_omega_step(wide[:, :p].contiguous(), beta, 1.0, random_state=(9, 9))
+    assert torch.equal(om3, om4) and torch.equal(G3, G4)
+    with pytest.raises(ValueError):
+        logistic_omega_step(torch.zeros(4, 65, device="cuda", dtype=torch.float64), torch.zeros(65))

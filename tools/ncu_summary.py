@@ -36,6 +36,14 @@ KEYS = [
     ("dram_read", "dram__bytes_read.sum"),
     ("dram_write", "dram__bytes_write.sum"),
     ("dram_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+    ("lsu_pipe_pct", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+    ("smem_wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+    ("smem_wavefronts_pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed"),
+    ("smem_ld_bank_conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum"),
+    ("smem_st_bank_conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum"),
+    ("stall_barrier", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"),
+    ("stall_mio_throttle", "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio"),
+    ("stall_lg_throttle", "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio"),
 ]
 
 

@@ -1,6 +1,6 @@
 """Run ONE BASELINE config a few times (for ncu: `ncu -k regex:... python tools/profile_case.py cfg2`).
 
-cases: cfg1 cfg2 cfg3_devroye cfg3_alternate cfg3_saddle cfg3_gamma cfg4 pdf logpdf cdf logcdf
+cases: cfg1 cfg2 cfg3_devroye cfg3_alternate cfg3_saddle cfg3_gamma cfg4 pdf logpdf cdf logcdf gibbs<p>
 """
 import os
 import sys
@@ -23,6 +23,18 @@ zN = torch.randn(n, device=dev, dtype=torch.float64, generator=g) * 3
 out = torch.empty(n, device=dev, dtype=torch.float64)
 rs = (12345, 0)
 kw = dict(out=out, random_state=rs, disable_checks=True)
+if case.startswith("gibbs"):
+    from polyagamma_b200.gibbs import logistic_omega_step
+
+    p = int(case[5:])
+    rows = n * 8 // p
+    X = torch.randn(rows, p, device=dev, dtype=torch.float64, generator=g)
+    beta = torch.randn(p, device=dev, dtype=torch.float64, generator=g) * (3.0 / p**0.5)
+    for _ in range(reps):
+        logistic_omega_step(X, beta, 1.0, random_state=rs)
+    torch.cuda.synchronize()
+    print("done", case, rows)
+    sys.exit(0)
 run = {
     "cfg1": lambda: pg.random_polyagamma(1.0, 0.0, size=n, device=dev, random_state=rs),
     "cfg2": lambda: pg.random_polyagamma(1.0, zN, **kw),
