@@ -110,6 +110,12 @@ int pgm_cuda_polyagamma_density_strided(int which, const double* d_x, const doub
                                         const int64_t* x_strides, const int64_t* h_strides,
                                         const int64_t* z_strides, double* d_out, void* stream);
 
+/* Host-buffer form of the four density functions (which: 0 pdf, 1 cdf, 2 logpdf, 3 logcdf): x, h, z, out
+ * are HOST arrays; a stride of 0 broadcasts a single value, 1 walks a contiguous array of n.  Chunked
+ * H2D -> kernel -> D2H on a private stream; returns after `out` is complete.  device < 0: current. */
+int pgm_cuda_polyagamma_density_host(int which, const double* x, int x_stride, const double* h, int h_stride,
+                                     const double* z, int z_stride, size_t n, double* out, int device);
+
 /* ---- next row of the path: the logistic-regression Gibbs omega-step ---------- */
 /* The caller pattern of the batched fill (README.md:146-148; Polson, Scott & Windle 2013):
  *     psi = X beta;   omega_i ~ PG(n_i, psi_i);   G = X^T diag(omega) X

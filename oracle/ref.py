@@ -121,3 +121,28 @@ def c_density(name, x, h, z):
     for i, (a, b, c) in enumerate(zip(xb.reshape(-1), hb.reshape(-1), zb.reshape(-1))):
         of[i] = f(a, b, c)
     return out
+
+
+_shim_mod = None
+
+
+def shim_module_available() -> bool:
+    return bool(glob.glob(os.path.join(_HERE, "_ref_shim", "_polyagamma*.so")))
+
+
+def shim_module():
+    """The reference's Cython front-end linked against polyagamma_b200/libpgm_cuda_shim.so instead
+    of the reference's C sources (``make -C oracle ref_shim``): its ``rvs``/``pdf``/``cdf`` run on
+    the GPU.  Used by tests/test_gpu_shim.py only ("switch by relinking")."""
+    global _shim_mod
+    if _shim_mod is None:
+        paths = glob.glob(os.path.join(_HERE, "_ref_shim", "_polyagamma*.so"))
+        if not paths:
+            raise ImportError("oracle/_ref_shim/_polyagamma*.so missing: run `make -C oracle ref_shim`")
+        # a distinct module name keeps it apart from the CPU build loaded by module(); the init
+        # symbol is still PyInit__polyagamma, which spec_from_file_location derives from the name
+        # after the last dot
+        spec = importlib.util.spec_from_file_location("pgm_shim_linked._polyagamma", paths[0])
+        _shim_mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_shim_mod)
+    return _shim_mod

@@ -459,4 +459,57 @@ pgm_cuda_polyagamma_density_strided(int which, const double* d_x, const double* 
     return launch_density(which, a, n, (cudaStream_t)stream);
 }
 
+int
+pgm_cuda_polyagamma_density_host(int which, const double* x, int x_stride, const double* h, int h_stride,
+                                 const double* z, int z_stride, size_t n, double* out, int device)
+{
+    if (which < 0 || which > 3) return PGM_CUDA_EINVAL;
+    if (n == 0) return 0;
+    if (x == nullptr || h == nullptr || z == nullptr || out == nullptr) return PGM_CUDA_EINVAL;
+    const int strides[3] = {x_stride, h_stride, z_stride};
+    for (int k = 0; k < 3; ++k)
+        if (strides[k] != 0 && strides[k] != 1) return PGM_CUDA_EINVAL;
+    DeviceGuard guard(device);
+    cudaStream_t s = nullptr;
+    cudaError_t e;
+    if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+    const size_t chunk = n < kHostChunk ? n : kHostChunk;
+    const double* src[3] = {x, h, z};
+    double* d[4] = {nullptr, nullptr, nullptr, nullptr};
+    int rc = 0;
+    for (int k = 0; k < 4 && rc == 0; ++k) {
+        const size_t len = (k < 3 && strides[k] == 0) ? 1 : chunk;
+        rc = (int)cudaMallocAsync(&d[k], len * sizeof(double), s);
+    }
+    for (int k = 0; k < 3 && rc == 0; ++k)
+        if (strides[k] == 0) rc = (int)cudaMemcpyAsync(d[k], src[k], sizeof(double), cudaMemcpyHostToDevice, s);
+    for (size_t off = 0; off < n && rc == 0; off += chunk) {
+        const size_t cn = (n - off) < chunk ? (n - off) : chunk;
+        for (int k = 0; k < 3 && rc == 0; ++k)
+            if (strides[k] == 1)
+                rc = (int)cudaMemcpyAsync(d[k], src[k] + off, cn * sizeof(double), cudaMemcpyHostToDevice, s);
+        if (rc != 0) break;
+        DensityArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x = d[0];
+        a.h = d[1];
+        a.z = d[2];
+        a.out = d[3];
+        if (!(x_stride == 1 && h_stride == 1 && z_stride == 1)) {
+            a.bc.ndim = 1;
+            a.bc.shape[0] = (int64_t)cn;
+            a.bc.xs[0] = x_stride;
+            a.bc.hs[0] = h_stride;
+            a.bc.zs[0] = z_stride;
+        }
+        rc = launch_density(which, a, cn, s);
+        if (rc == 0) rc = (int)cudaMemcpyAsync(out + off, d[3], cn * sizeof(double), cudaMemcpyDeviceToHost, s);
+    }
+    for (int k = 0; k < 4; ++k)
+        if (d[k]) cudaFreeAsync(d[k], s);
+    e = cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    return rc != 0 ? rc : (int)e;
+}
+
 }  // extern "C"
