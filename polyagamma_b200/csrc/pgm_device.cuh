@@ -238,6 +238,16 @@ sincos2pi(double u, double& s_out, double& c_out)
 // registers and are shifted down on every draw (no local-memory indexing).
 // OUTLINE: keep ONE copy of the block function per kernel (persistent samplers: many call sites,
 // instruction-cache bound) or inline it (dense kernels with a single draw site).
+// The outlined copy takes and returns VALUES: a member function would take the address of the
+// generator and force its state into local memory (STL/LDL around every call).
+static __device__ __noinline__ uint4
+philox_block_outlined(uint32_t i0, uint32_t i1, uint32_t blk, uint32_t k0, uint32_t k1)
+{
+    uint32_t b0 = i0, b1 = i1, b2 = blk, b3 = 0;
+    philox4x32_10(b0, b1, b2, b3, k0, k1);
+    return make_uint4(b0, b1, b2, b3);
+}
+
 template <bool OUTLINE>
 struct RngT {
     uint32_t k0, k1, i0, i1, blk;
@@ -258,22 +268,27 @@ struct RngT {
     // samplers and the persistent kernels live or die by their instruction-cache footprint.
     __device__ __forceinline__ void refill_body()
     {
-        b0 = i0;
-        b1 = i1;
-        b2 = blk;
-        b3 = 0;
-        philox4x32_10(b0, b1, b2, b3, k0, k1);
+        if (OUTLINE) {
+            const uint4 w = philox_block_outlined(i0, i1, blk, k0, k1);
+            b0 = w.x;
+            b1 = w.y;
+            b2 = w.z;
+            b3 = w.w;
+        }
+        else {
+            b0 = i0;
+            b1 = i1;
+            b2 = blk;
+            b3 = 0;
+            philox4x32_10(b0, b1, b2, b3, k0, k1);
+        }
         ++blk;
         left = 4;
     }
-    __device__ __noinline__ void refill_outlined() { refill_body(); }
 
     __device__ __forceinline__ uint32_t u32()
     {
-        if (left == 0) {
-            if (OUTLINE) refill_outlined();
-            else refill_body();
-        }
+        if (left == 0) refill_body();
         uint32_t w = b0;
         b0 = b1;
         b1 = b2;
