@@ -3,12 +3,11 @@
 // Replaces src/pgm_random.c:144-180 (pgm_random_polyagamma / _fill / _fill2 and the hybrid
 // dispatch).  Pipeline for one chunk of the output index range:
 //
-//   hybrid:   classify_kernel   method id per element (+ NaN/inf for invalid h), per-block
-//                               histograms
-//             scan_kernel       exclusive scan of the histograms -> per-method list bases
-//             scatter_kernel    ascending per-method element lists (one u32 per element)
-//             per method        persistent_kernel<M> / dense_kernel over that method's list
-//   explicit: persistent_kernel<M> / dense_kernel over the identity list
+//   hybrid:   bucket_kernel     one pass: bucket id per element (+ NaN/inf for invalid h), one list
+//                               reservation per bucket and block, per-bucket element lists
+//             per bucket        setup_kernel<M> (per-element records) + sample_kernel<M>, or
+//                               dense_kernel, over that bucket's list
+//   explicit: the same kernels over the identity list
 //
 // persistent_kernel: every lane owns one element at a time and advances it by ONE proposal
 // attempt per loop trip (pgm_methods.cuh); lanes whose element completed are retired and
@@ -150,8 +149,8 @@ constexpr uint8_t kBucketNone = 255;
 enum : int { kBDevroye = 0, kBAlternate = 1, kBSaddleFull = 2, kBSaddleLeft = 3, kBSaddleFar = 4, kBAlternateLeft = 5,
              kBSaddleMid = 6, kBNormal = 7, kNumBuckets = 8, kBGamma = 8 };
 
-// ctl layout (uint32): [0..7] bucket counts, [8..15] list bases, [16..23] work counters
-constexpr int kCtlCount = 0, kCtlBase = 8, kCtlWork = 16, kCtlWords = 32;
+// ctl layout (uint32): [0..7] bucket counts, [8..15] record bases, [16..23] work counters, [24] ticket
+constexpr int kCtlCount = 0, kCtlBase = 8, kCtlWork = 16, kCtlTicket = 24, kCtlWords = 32;
 
 __host__ __device__ __forceinline__ int
 bucket_of(int method, double h, double z, bool compat)
@@ -173,10 +172,10 @@ bucket_of(int method, double h, double z, bool compat)
 
 // Layout of the pre-pass: a block owns kTilesPerBlock consecutive tiles of kBucketTile elements;
 // thread t of a tile owns the 8 CONSECUTIVE elements tile*2048 + t*8 .. +7, so h and z are read
-// with 16-byte loads, the 8 bucket ids are stored as one 8-byte word, and every per-method list
-// comes out in ascending element order.  Per-bucket counts travel packed two to a 32-bit word
-// (16 bits each; a block never holds more than 8192 elements).
-constexpr int kTilesPerBlock = 4;
+// with 16-byte loads and the 8 bucket ids are stored as one 8-byte word.  Per-bucket counts travel
+// packed two to a 32-bit word (16 bits each; a block holds kTilesPerBlock * 2048 <= 8192 elements).
+// Measured on cfg4 (ms per 1e9 elements): 1 tile 5.13, 2 tiles 4.64, 4 tiles 4.87, 8 tiles 8.9.
+constexpr int kTilesPerBlock = 2;
 constexpr int kPacked = (kNumBuckets + 1) / 2;
 
 __device__ __forceinline__ void
@@ -194,98 +193,105 @@ packed_get(const uint32_t (&pc)[kPacked], int q)
     return (q & 1) ? (pc[q >> 1] >> 16) : (pc[q >> 1] & 0xffffu);
 }
 
+// One pass builds the per-method element lists.  Phase 1: every thread classifies its 8 elements of
+// each of the block's tiles (all loads of the block are in flight together) and stores the 8 bucket
+// ids as one 64-bit word in shared memory.  The block's per-bucket totals then reserve a
+// range of each bucket's list with ONE atomicAdd per bucket and block (ctl[kCtlCount + q] ends up as
+// the bucket's length).  Phase 2 re-reads the ids from shared memory in striped order and writes the
+// element indices.  Bucket q's list is list + q * list_stride; the order of the entries inside a
+// block's range and of the blocks' ranges depends on scheduling, which changes which lane draws an
+// element, never what is drawn (private Philox stream per element).
+// The last block to finish (ticket counter, no spinning) turns the totals into the record bases.
 // `method` is the requested sampler (kHybrid: src/pgm_random.c:105-121 decides per element).
 // VEC: h and z are contiguous, 16-byte aligned arrays (or scalars).
 template <bool VEC>
 __global__ void __launch_bounds__(kBucketThreads)
-classify_kernel(FillArgs a, uint32_t n, int method, uint8_t* __restrict__ meth, uint32_t* __restrict__ block_counts)
+bucket_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, uint32_t* __restrict__ list,
+              uint32_t list_stride)
 {
+    static_assert(kNumBuckets <= 8 && kPacked == 4, "offsets are packed 4 x 16 bit into two 64-bit words");
     __shared__ uint32_t s_cnt[kPacked];
+    __shared__ uint32_t s_run[8];  // next free list slot of each bucket for this block
+    __shared__ __align__(8) uint8_t s_meth[kTilesPerBlock][kBucketTile];
+    const uint32_t lane = threadIdx.x & 31;
     if (threadIdx.x < kPacked) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const bool compat = a.compat != 0;
     uint32_t pc[kPacked];
 #pragma unroll
     for (int w = 0; w < kPacked; ++w) pc[w] = 0;
+#pragma unroll
     for (int tile = 0; tile < kTilesPerBlock; ++tile) {
         const uint32_t e0 = (blockIdx.x * kTilesPerBlock + tile) * kBucketTile + threadIdx.x * kBucketItems;
-        if (e0 >= n) break;
-        const bool full = (e0 + kBucketItems <= n);
-        uint64_t word = 0;
-        auto classify_one = [&](int k, double h, double z) {
-            uint32_t b = kBucketNone;
-            double bad;
-            if (invalid_h(h, bad)) {
-                a.out[a.base + e0 + k] = bad;
-            }
-            else {
-                int m = (method == kHybrid) ? hybrid_select(h, z) : method;
-                b = (uint32_t)bucket_of(m, h, z, compat);
-                packed_add(pc, (int)b);
-            }
-            word |= (uint64_t)b << (8 * k);
-        };
-        if (VEC && full) {
-            double hv[kBucketItems], zv[kBucketItems];
-            const uint64_t g0 = a.base + e0;
-            if (a.h) {
-                const double2* p = reinterpret_cast<const double2*>(a.h + g0);
-#pragma unroll
-                for (int k = 0; k < kBucketItems / 2; ++k) {
-                    double2 v = __ldg(p + k);
-                    hv[2 * k] = v.x;
-                    hv[2 * k + 1] = v.y;
-                }
-            }
-            else {
-#pragma unroll
-                for (int k = 0; k < kBucketItems; ++k) hv[k] = a.h_scalar;
-            }
-            if (a.z) {
-                const double2* p = reinterpret_cast<const double2*>(a.z + g0);
-#pragma unroll
-                for (int k = 0; k < kBucketItems / 2; ++k) {
-                    double2 v = __ldg(p + k);
-                    zv[2 * k] = v.x;
-                    zv[2 * k + 1] = v.y;
-                }
-            }
-            else {
-#pragma unroll
-                for (int k = 0; k < kBucketItems; ++k) zv[k] = a.z_scalar;
-            }
-#pragma unroll
-            for (int k = 0; k < kBucketItems; ++k) classify_one(k, hv[k], zv[k]);
-        }
-        else {
-#pragma unroll 1
-            for (int k = 0; k < kBucketItems; ++k) {
-                if (e0 + k < n) {
-                    double h, z;
-                    load_hz(a, a.base + e0 + k, h, z);
-                    classify_one(k, h, z);
+        uint64_t word = ~0ull;  // kBucketNone in every slot
+        if (e0 < n) {
+            const bool full = (e0 + kBucketItems <= n);
+            auto classify_one = [&](int k, double h, double z) {
+                uint32_t b = kBucketNone;
+                double bad;
+                if (invalid_h(h, bad)) {
+                    a.out[a.base + e0 + k] = bad;
                 }
                 else {
-                    word |= (uint64_t)kBucketNone << (8 * k);
+                    int m = (method == kHybrid) ? hybrid_select(h, z) : method;
+                    b = (uint32_t)bucket_of(m, h, z, compat);
+                    packed_add(pc, (int)b);
+                }
+                word = (word & ~(0xffull << (8 * k))) | ((uint64_t)b << (8 * k));
+            };
+            if (VEC && full) {
+                double hv[kBucketItems], zv[kBucketItems];
+                const uint64_t g0 = a.base + e0;
+                if (a.h) {
+                    const double2* p = reinterpret_cast<const double2*>(a.h + g0);
+#pragma unroll
+                    for (int k = 0; k < kBucketItems / 2; ++k) {
+                        double2 v = __ldg(p + k);
+                        hv[2 * k] = v.x;
+                        hv[2 * k + 1] = v.y;
+                    }
+                }
+                else {
+#pragma unroll
+                    for (int k = 0; k < kBucketItems; ++k) hv[k] = a.h_scalar;
+                }
+                if (a.z) {
+                    const double2* p = reinterpret_cast<const double2*>(a.z + g0);
+#pragma unroll
+                    for (int k = 0; k < kBucketItems / 2; ++k) {
+                        double2 v = __ldg(p + k);
+                        zv[2 * k] = v.x;
+                        zv[2 * k + 1] = v.y;
+                    }
+                }
+                else {
+#pragma unroll
+                    for (int k = 0; k < kBucketItems; ++k) zv[k] = a.z_scalar;
+                }
+#pragma unroll
+                for (int k = 0; k < kBucketItems; ++k) classify_one(k, hv[k], zv[k]);
+            }
+            else {
+#pragma unroll 1
+                for (int k = 0; k < kBucketItems; ++k) {
+                    if (e0 + k < n) {
+                        double h, z;
+                        load_hz(a, a.base + e0 + k, h, z);
+                        classify_one(k, h, z);
+                    }
                 }
             }
         }
-        if (full) {
-            *reinterpret_cast<uint64_t*>(meth + e0) = word;
-        }
-        else {
-#pragma unroll
-            for (int k = 0; k < kBucketItems; ++k) {
-                if (e0 + k < n) meth[e0 + k] = (uint8_t)(word >> (8 * k));
-            }
-        }
+        *reinterpret_cast<uint64_t*>(&s_meth[tile][threadIdx.x * kBucketItems]) = word;
     }
+    // block totals -> one reservation per bucket
 #pragma unroll
     for (int w = 0; w < kPacked; ++w) {
-        // a warp holds at most 256 * kTilesPerBlock... per thread at most 32: sums stay < 2^16
+        // a thread holds at most 8 * kTilesPerBlock <= 32 elements, a warp 1024: the packed 16-bit sums
+        // cannot carry
         for (int off = 16; off > 0; off >>= 1) pc[w] += __shfl_xor_sync(0xffffffffu, pc[w], off);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
 #pragma unroll
         for (int w = 0; w < kPacked; ++w) atomicAdd(&s_cnt[w], pc[w]);
     }
@@ -293,142 +299,44 @@ classify_kernel(FillArgs a, uint32_t n, int method, uint8_t* __restrict__ meth, 
     if (threadIdx.x < kNumBuckets) {
         uint32_t v = s_cnt[threadIdx.x >> 1];
         v = (threadIdx.x & 1) ? (v >> 16) : (v & 0xffffu);
-        block_counts[threadIdx.x * gridDim.x + blockIdx.x] = v;  // bucket-major
+        const uint32_t base = v ? atomicAdd(&ctl[kCtlCount + threadIdx.x], v) : 0u;
+        s_run[threadIdx.x] = threadIdx.x * list_stride + base;
     }
-}
-
-// One block: exclusive scan over the pre-pass blocks for each bucket (block_counts is
-// bucket-major: [bucket][block]); totals and list bases into ctl.
-__global__ void __launch_bounds__(1024)
-scan_kernel(const uint32_t* __restrict__ block_counts, uint32_t nblocks, uint32_t* __restrict__ block_offsets,
-            uint32_t* __restrict__ ctl)
-{
-    __shared__ uint32_t s_warp[32][kNumBuckets];
-    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t per = (nblocks + 1023) / 1024;
-    const uint32_t lo = min(t * per, nblocks), hi = min(lo + per, nblocks);
-    uint32_t sum[kNumBuckets], incl[kNumBuckets];
+    __syncthreads();  // s_run and s_meth are visible
+    // Phase 2, striped: lane t of stripe j takes element t0 + 256 j + t, so the lanes of a warp that
+    // share a bucket are consecutive elements and get consecutive list slots (coalesced stores).
+    // The lanes of each bucket are found with one MATCH.ANY on the bucket id; the lowest lane of a
+    // group reserves the group's slots from the block's running counter.
+    const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int q = 0; q < kNumBuckets; ++q) {
-        uint32_t v = 0;
-        for (uint32_t b = lo; b < hi; ++b) v += block_counts[q * nblocks + b];
-        sum[q] = v;
-        for (int off = 1; off < 32; off <<= 1) {
-            uint32_t up = __shfl_up_sync(0xffffffffu, v, off);
-            if (lane >= (uint32_t)off) v += up;
-        }
-        incl[q] = v;
-        if (lane == 31) s_warp[warp][q] = v;
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int q = 0; q < kNumBuckets; ++q) {
-            uint32_t v = s_warp[lane][q];
-            for (int off = 1; off < 32; off <<= 1) {
-                uint32_t up = __shfl_up_sync(0xffffffffu, v, off);
-                if (lane >= (uint32_t)off) v += up;
-            }
-            s_warp[lane][q] = v;  // inclusive over warps
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < kNumBuckets; ++q) {
-        uint32_t run = incl[q] - sum[q] + (warp ? s_warp[warp - 1][q] : 0u);  // exclusive prefix of thread t
-        for (uint32_t b = lo; b < hi; ++b) {
-            block_offsets[q * nblocks + b] = run;
-            run += block_counts[q * nblocks + b];
-        }
-    }
-    if (t == 0) {
-        uint32_t base = 0;
-#pragma unroll
-        for (int q = 0; q < kNumBuckets; ++q) {
-            uint32_t total = s_warp[31][q];
-            ctl[kCtlCount + q] = total;
-            ctl[kCtlBase + q] = base;
-            base += total;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kBucketThreads)
-scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __restrict__ block_offsets,
-               const uint32_t* __restrict__ ctl, uint32_t* __restrict__ list)
-{
-    static_assert(kNumBuckets <= 8 && kPacked == 4, "offsets are packed 4 x 16 bit into two 64-bit words");
-    __shared__ uint32_t s_warp[kBucketThreads / 32][kPacked];
-    __shared__ uint32_t s_run[8];  // next free list slot of each bucket for this block
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x < kNumBuckets) {
-        s_run[threadIdx.x] = ctl[kCtlBase + threadIdx.x] + block_offsets[threadIdx.x * gridDim.x + blockIdx.x];
-    }
     for (int tile = 0; tile < kTilesPerBlock; ++tile) {
         const uint32_t t0 = (blockIdx.x * kTilesPerBlock + tile) * kBucketTile;
         if (t0 >= n) break;  // block-uniform
-        const uint32_t e0 = t0 + threadIdx.x * kBucketItems;
-        uint64_t word = ~0ull;
-        if (e0 + kBucketItems <= n) {
-            word = *reinterpret_cast<const uint64_t*>(meth + e0);
-        }
-        else {
 #pragma unroll
-            for (int k = 0; k < kBucketItems; ++k) {
-                if (e0 + k < n) word = (word & ~(0xffull << (8 * k))) | ((uint64_t)meth[e0 + k] << (8 * k));
+        for (int j = 0; j < kBucketItems; ++j) {
+            const uint32_t i = j * kBucketThreads + threadIdx.x;
+            const uint32_t q = s_meth[tile][i];
+            const bool valid = q < (uint32_t)kNumBuckets;
+            const uint32_t same = __match_any_sync(0xffffffffu, q);
+            const int leader = __ffs(same) - 1;
+            uint32_t slot = 0;
+            if (valid && (int)lane == leader) slot = atomicAdd(&s_run[q], (uint32_t)__popc(same));
+            slot = __shfl_sync(0xffffffffu, slot, leader < 0 ? 0 : leader);
+            if (valid) list[slot + __popc(same & lt)] = t0 + i;
+        }
+    }
+    // the last block turns the bucket totals into the bases of the packed record regions
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t ticket = atomicAdd(&ctl[kCtlTicket], 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            uint32_t base = 0;
+            for (int q = 0; q < kNumBuckets; ++q) {
+                ctl[kCtlBase + q] = base;
+                base += atomicAdd(&ctl[kCtlCount + q], 0u);
             }
         }
-        uint32_t pc[kPacked];
-#pragma unroll
-        for (int w = 0; w < kPacked; ++w) pc[w] = 0;
-#pragma unroll
-        for (int k = 0; k < kBucketItems; ++k) packed_add(pc, (int)((word >> (8 * k)) & 0xff));
-        uint32_t incl[kPacked];
-#pragma unroll
-        for (int w = 0; w < kPacked; ++w) {
-            uint32_t v = pc[w];
-            for (int off = 1; off < 32; off <<= 1) {
-                uint32_t up = __shfl_up_sync(0xffffffffu, v, off);
-                if (lane >= (uint32_t)off) v += up;
-            }
-            incl[w] = v;
-            if (lane == 31) s_warp[warp][w] = v;
-        }
-        __syncthreads();  // s_warp of this tile and s_run of the previous tile are visible
-        uint32_t before[kPacked], total[kPacked];
-#pragma unroll
-        for (int w = 0; w < kPacked; ++w) {
-            uint32_t bsum = 0, tsum = 0;
-            for (uint32_t ww = 0; ww < kBucketThreads / 32; ++ww) {
-                uint32_t v = s_warp[ww][w];
-                tsum += v;
-                if (ww < warp) bsum += v;
-            }
-            before[w] = bsum + incl[w] - pc[w];  // elements of this tile ahead of this thread
-            total[w] = tsum;
-        }
-        // per-item destination: bucket base (shared memory) + this thread's running 16-bit offset
-        // of that bucket, kept four to a 64-bit word
-        uint64_t lo = (uint64_t)before[0] | ((uint64_t)before[1] << 32);
-        uint64_t hi = (uint64_t)before[2] | ((uint64_t)before[3] << 32);
-#pragma unroll
-        for (int k = 0; k < kBucketItems; ++k) {
-            const uint32_t q = (uint32_t)(word >> (8 * k)) & 0xffu;
-            if (q < (uint32_t)kNumBuckets) {
-                const uint32_t sh = (q & 3u) * 16u;
-                const uint64_t sel = (q & 4u) ? hi : lo;
-                list[s_run[q] + (uint32_t)((sel >> sh) & 0xffffu)] = e0 + k;
-                if (q & 4u) hi += 1ull << sh;
-                else lo += 1ull << sh;
-            }
-        }
-        __syncthreads();  // every thread has read s_run
-        uint32_t mine = 0;
-#pragma unroll
-        for (int q = 0; q < kNumBuckets; ++q) {
-            if (threadIdx.x == (uint32_t)q) mine = packed_get(total, q);
-        }
-        if (threadIdx.x < kNumBuckets) s_run[threadIdx.x] += mine;
     }
 }
 
@@ -436,12 +344,14 @@ scatter_kernel(const uint8_t* __restrict__ meth, uint32_t n, const uint32_t* __r
 // work description shared by the per-method kernels
 // ---------------------------------------------------------------------------------------
 // A bucket is either the identity range [0, count_imm) of the chunk (ctl == nullptr) or the
-// bucket-th sub-list of `list`, whose length and base live in ctl on the device.
+// bucket-th list (list + bucket * list_stride), whose length and record base live in ctl on the
+// device.
 struct Bucket {
     const uint32_t* list;
     const uint32_t* ctl;
     int bucket;
     uint32_t count_imm;
+    uint32_t list_stride;  // bucket q's list starts at list + q * list_stride
     double* params;  // record storage for this chunk (kMaxRecordFields doubles per element)
     int uniform;     // 1: one record (position 0) serves every element (scalar h and z)
 };
@@ -463,7 +373,7 @@ view_of(const Bucket& b)
     if (b.ctl) {
         uint32_t base = b.ctl[kCtlBase + b.bucket];
         v.count = b.ctl[kCtlCount + b.bucket];
-        v.list = b.list + base;
+        v.list = b.list + (size_t)b.bucket * b.list_stride;
         v.recs = b.params + (size_t)base * kMaxRecordFields;
     }
     v.stride = b.uniform ? 1u : v.count;
@@ -584,17 +494,30 @@ dense_kernel(FillArgs a, Bucket b)
     const BucketView v = view_of(b);
     const uint32_t stride = gridDim.x * blockDim.x;
     if (KIND == kNormal) {
-        // two elements per trip: both gathers (list index -> h, z) are in flight before either
-        // element's arithmetic starts, and the two dependency chains interleave
-        for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < v.count; pos += 2 * stride) {
-            const uint32_t pos1 = pos + stride;
-            const bool two = pos1 < v.count;
-            const uint32_t e0 = v.list ? v.list[pos] : pos;
-            const uint32_t e1 = two ? (v.list ? v.list[pos1] : pos1) : e0;
+        // Two elements per trip (their dependency chains interleave), software-pipelined two deep:
+        // the list indices of trip t + 2 and the (h, z) gathers of trip t + 1 are issued before
+        // trip t's arithmetic, so the two dependent memory round trips never sit on the
+        // critical path.  Positions past the end are clamped (valid loads, results unused).
+        if (v.count == 0) return;
+        const uint32_t last = v.count - 1;
+        auto entry = [&](uint32_t p) -> uint32_t {
+            p = min(p, last);
+            return v.list ? v.list[p] : p;
+        };
+        uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+        uint32_t e0 = entry(pos), e1 = entry(pos + stride);
+        uint32_t n0 = entry(pos + 2 * stride), n1 = entry(pos + 3 * stride);
+        double h0, z0, h1, z1;
+        load_hz(a, a.base + e0, h0, z0);
+        load_hz(a, a.base + e1, h1, z1);
+        for (; pos < v.count; pos += 2 * stride) {
+            const bool two = pos + stride < v.count;
+            const uint32_t m0 = entry(pos + 4 * stride), m1 = entry(pos + 5 * stride);
+            double hn0, zn0, hn1, zn1;
+            load_hz(a, a.base + n0, hn0, zn0);
+            load_hz(a, a.base + n1, hn1, zn1);
             const uint64_t g0 = a.base + e0, g1 = a.base + e1;
-            double h0, z0, h1, z1, bad;
-            load_hz(a, g0, h0, z0);
-            load_hz(a, g1, h1, z1);
+            double bad;
             RngInline r0, r1;
             r0.init(a.key, a.first_index + g0);
             r1.init(a.key, a.first_index + g1);
@@ -604,6 +527,8 @@ dense_kernel(FillArgs a, Bucket b)
                 const double s1 = invalid_h(h1, bad) ? bad : normal_approx_sample(r1, h1, z1);
                 a.out[g1] = s1;
             }
+            e0 = n0, e1 = n1, n0 = m0, n1 = m1;
+            h0 = hn0, z0 = zn0, h1 = hn1, z1 = zn1;
         }
         return;
     }
@@ -823,7 +748,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
             const uint64_t off = c * kChunk;
             const uint32_t cn = (uint32_t)((n - off) < kChunk ? (n - off) : kChunk);
             a.base = base0 + off;
-            Bucket b{nullptr, nullptr, bk, cn, params, 1};
+            Bucket b{nullptr, nullptr, bk, cn, 0, params, 1};
             switch (bk) {
                 case kBDevroye: launch_method<Devroye>(d, 0, a, b, cn, counters + c, s); break;
                 case kBAlternate: launch_method<Alternate>(d, 1, a, b, cn, counters + c, s); break;
@@ -851,19 +776,19 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     const bool overlap = bucketed && n > (1ull << lg) && getenv("PGM_CUDA_NO_OVERLAP") == nullptr;
     const int nprep = overlap ? 2 : 1;
     uint64_t chunk = 0;
-    size_t list_bytes = 0, meth_bytes = 0, hist_bytes = 0, par_bytes = 0, prep_bytes = 0;
+    size_t list_bytes = 0, par_bytes = 0, prep_bytes = 0;
+    uint32_t list_stride = 0;
     const size_t ctl_bytes = align256(kCtlWords * sizeof(uint32_t));
     char* ws = nullptr;
     for (;;) {
         chunk = 1ull << lg;
         const uint64_t cmax = n < chunk ? n : chunk;
-        const uint32_t nblocks_max =
-            (uint32_t)((cmax + kBucketTile * kTilesPerBlock - 1) / (kBucketTile * kTilesPerBlock));
-        list_bytes = bucketed ? align256(cmax * sizeof(uint32_t)) : 0;
-        meth_bytes = bucketed ? align256(cmax) : 0;
-        hist_bytes = bucketed ? align256((size_t)nblocks_max * kNumBuckets * sizeof(uint32_t)) : 0;
+        // one worst-case list per bucket (the single-pass bucketing cannot know the bucket sizes
+        // before it writes): 32 B of scratch per element next to the 72 B of records
+        list_stride = (uint32_t)((cmax + 63) & ~uint64_t(63));
+        list_bytes = bucketed ? align256((size_t)list_stride * kNumBuckets * sizeof(uint32_t)) : 0;
         par_bytes = (m == kGamma) ? 0 : align256(cmax * kMaxRecordFields * sizeof(double));
-        prep_bytes = list_bytes + meth_bytes + 2 * hist_bytes + ctl_bytes;
+        prep_bytes = list_bytes + ctl_bytes;
         err = cudaMallocAsync(&ws, nprep * prep_bytes + par_bytes, s);
         if (err == cudaSuccess) break;
         (void)cudaGetLastError();  // clear the sticky-free allocation error and retry smaller
@@ -871,17 +796,12 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         --lg;
     }
     struct Prep {
-        uint32_t* list;
-        uint8_t* meth;
-        uint32_t *block_counts, *block_offsets, *ctl;
+        uint32_t *list, *ctl;
     } prep[2];
     for (int i = 0; i < nprep; ++i) {
         char* base = ws + (size_t)i * prep_bytes;
         prep[i].list = (uint32_t*)base;
-        prep[i].meth = (uint8_t*)(base + list_bytes);
-        prep[i].block_counts = (uint32_t*)(base + list_bytes + meth_bytes);
-        prep[i].block_offsets = (uint32_t*)(base + list_bytes + meth_bytes + hist_bytes);
-        prep[i].ctl = (uint32_t*)(base + list_bytes + meth_bytes + 2 * hist_bytes);
+        prep[i].ctl = (uint32_t*)(base + list_bytes);
     }
     if (nprep == 1) prep[1] = prep[0];
     double* params = (double*)(ws + (size_t)nprep * prep_bytes);
@@ -898,7 +818,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
             const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
             a.base = base0 + off;
             cudaMemsetAsync(ctl, 0, ctl_bytes, s);
-            Bucket b{nullptr, nullptr, 0, cn, params, 0};
+            Bucket b{nullptr, nullptr, 0, cn, 0, params, 0};
             switch (m) {
                 case kDevroye: launch_method<Devroye>(d, 0, a, b, cn, ctl + kCtlWork, s); break;
                 default: launch_dense<kGamma>(d, a, b, cn, s); break;
@@ -914,22 +834,10 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         cudaMemsetAsync(pp.ctl, 0, ctl_bytes, sb);
         {
             ScopedKernelTimer timer(kKindClassify, sb);
-            if (vec) {
-                classify_kernel<true><<<nblocks, kBucketThreads, 0, sb>>>(ap, cn, m, pp.meth, pp.block_counts);
-            }
-            else {
-                classify_kernel<false><<<nblocks, kBucketThreads, 0, sb>>>(ap, cn, m, pp.meth, pp.block_counts);
-            }
+            if (vec) bucket_kernel<true><<<nblocks, kBucketThreads, 0, sb>>>(ap, cn, m, pp.ctl, pp.list, list_stride);
+            else bucket_kernel<false><<<nblocks, kBucketThreads, 0, sb>>>(ap, cn, m, pp.ctl, pp.list, list_stride);
         }
-        {
-            ScopedKernelTimer timer(kKindScan, sb);
-            scan_kernel<<<1, 1024, 0, sb>>>(pp.block_counts, nblocks, pp.block_offsets, pp.ctl);
-        }
-        {
-            ScopedKernelTimer timer(kKindScatter, sb);
-            scatter_kernel<<<nblocks, kBucketThreads, 0, sb>>>(pp.meth, cn, pp.block_offsets, pp.ctl, pp.list);
-        }
-        count_launch(3);
+        count_launch(1);
     };
     // method kernels of one pass, on the caller's stream.  Counts and list bases stay on the
     // device: the kernels read them there, so the host never waits for the histogram (empty
@@ -939,7 +847,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     // launch tail, fill the tails of the others.  s1/s2 == s serialises everything on `s`.
     auto sampling = [&](const FillArgs& ap, uint32_t cn, const Prep& pp, cudaStream_t s1, cudaStream_t s2) {
         uint32_t* ctl = pp.ctl;
-        auto bucket = [&](int q) { return Bucket{pp.list, ctl, q, 0, params, 0}; };
+        auto bucket = [&](int q) { return Bucket{pp.list, ctl, q, 0, list_stride, params, 0}; };
         if (m != kAlternate) {
             launch_method<SaddleFar>(d, 4, ap, bucket(kBSaddleFar), cn, ctl + kCtlWork + kBSaddleFar, s);
             launch_method<SaddleFar>(d, 6, ap, bucket(kBSaddleMid), cn, ctl + kCtlWork + kBSaddleMid, s1);
