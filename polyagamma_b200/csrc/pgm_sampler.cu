@@ -487,6 +487,11 @@ sample_kernel(FillArgs a, Bucket b, uint32_t* __restrict__ counter)
 // ---------------------------------------------------------------------------------------
 // dense kernels: one pass, no outer rejection loop (normal approximation, gamma convolution)
 // ---------------------------------------------------------------------------------------
+#ifndef PGM_NORMAL_PER_TRIP
+#define PGM_NORMAL_PER_TRIP 2
+#endif
+constexpr int kNormalPerTrip = PGM_NORMAL_PER_TRIP;
+
 template <int KIND>
 __global__ void __launch_bounds__(256)
 dense_kernel(FillArgs a, Bucket b)
@@ -494,41 +499,52 @@ dense_kernel(FillArgs a, Bucket b)
     const BucketView v = view_of(b);
     const uint32_t stride = gridDim.x * blockDim.x;
     if (KIND == kNormal) {
-        // Two elements per trip (their dependency chains interleave), software-pipelined two deep:
-        // the list indices of trip t + 2 and the (h, z) gathers of trip t + 1 are issued before
-        // trip t's arithmetic, so the two dependent memory round trips never sit on the
-        // critical path.  Positions past the end are clamped (valid loads, results unused).
+        // kNormalPerTrip elements per trip (their dependency chains interleave and the constants of
+        // the polynomial kernels are fetched once per trip), software-pipelined two deep: the list
+        // indices of trip t + 2 and the (h, z) gathers of trip t + 1 are issued before trip t's
+        // arithmetic, so the two dependent memory round trips never sit on the critical path.
+        // Positions past the end are clamped (valid loads, results unused).
         if (v.count == 0) return;
+        constexpr int E = kNormalPerTrip;
         const uint32_t last = v.count - 1;
         auto entry = [&](uint32_t p) -> uint32_t {
             p = min(p, last);
             return v.list ? v.list[p] : p;
         };
         uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-        uint32_t e0 = entry(pos), e1 = entry(pos + stride);
-        uint32_t n0 = entry(pos + 2 * stride), n1 = entry(pos + 3 * stride);
-        double h0, z0, h1, z1;
-        load_hz(a, a.base + e0, h0, z0);
-        load_hz(a, a.base + e1, h1, z1);
-        for (; pos < v.count; pos += 2 * stride) {
-            const bool two = pos + stride < v.count;
-            const uint32_t m0 = entry(pos + 4 * stride), m1 = entry(pos + 5 * stride);
-            double hn0, zn0, hn1, zn1;
-            load_hz(a, a.base + n0, hn0, zn0);
-            load_hz(a, a.base + n1, hn1, zn1);
-            const uint64_t g0 = a.base + e0, g1 = a.base + e1;
-            double bad;
-            RngInline r0, r1;
-            r0.init(a.key, a.first_index + g0);
-            r1.init(a.key, a.first_index + g1);
-            const double s0 = invalid_h(h0, bad) ? bad : normal_approx_sample(r0, h0, z0);
-            a.out[g0] = s0;
-            if (two) {
-                const double s1 = invalid_h(h1, bad) ? bad : normal_approx_sample(r1, h1, z1);
-                a.out[g1] = s1;
+        uint32_t e[E], nx[E];
+        double h[E], z[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            e[i] = entry(pos + i * stride);
+            nx[i] = entry(pos + (E + i) * stride);
+        }
+#pragma unroll
+        for (int i = 0; i < E; ++i) load_hz(a, a.base + e[i], h[i], z[i]);
+        for (; pos < v.count; pos += E * stride) {
+            uint32_t nn[E];
+            double hn[E], zn[E];
+#pragma unroll
+            for (int i = 0; i < E; ++i) nn[i] = entry(pos + (2 * E + i) * stride);
+#pragma unroll
+            for (int i = 0; i < E; ++i) load_hz(a, a.base + nx[i], hn[i], zn[i]);
+            double out[E];
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                double bad;
+                RngInline r;
+                r.init(a.key, a.first_index + a.base + e[i]);
+                out[i] = invalid_h(h[i], bad) ? bad : normal_approx_sample(r, h[i], z[i]);
             }
-            e0 = n0, e1 = n1, n0 = m0, n1 = m1;
-            h0 = hn0, z0 = zn0, h1 = hn1, z1 = zn1;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                if (pos + i * stride < v.count) a.out[a.base + e[i]] = out[i];
+            }
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                e[i] = nx[i], nx[i] = nn[i];
+                h[i] = hn[i], z[i] = zn[i];
+            }
         }
         return;
     }
