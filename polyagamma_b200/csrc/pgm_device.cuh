@@ -23,9 +23,25 @@ constexpr double kLog2 = 0.6931471805599453094172321214581766;
 // ---------------------------------------------------------------------------------------
 // Philox4x32-10.  Host+device so the ABI layer derives the call key with the same code.
 // ---------------------------------------------------------------------------------------
+// rk: the ten round keys (k0 + r W0, k1 + r W1), precomputed on the host.  A kernel that inlines the
+// block function reads them straight from its parameter bank as instruction operands, instead of
+// issuing 18 uniform adds per block to bump the key.
 struct PhiloxKey {
     uint32_t k0, k1;
+    uint32_t rk[20];
 };
+
+__host__ __device__ __forceinline__ void
+philox_round_keys(PhiloxKey& key)
+{
+    uint32_t k0 = key.k0, k1 = key.k1;
+    for (int r = 0; r < 10; ++r) {
+        key.rk[2 * r] = k0;
+        key.rk[2 * r + 1] = k1;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
 
 __host__ __device__ __forceinline__ void
 philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1)
@@ -47,13 +63,35 @@ philox4x32_10(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k
     }
 }
 
+// the same ten rounds with the round keys given
+__device__ __forceinline__ void
+philox4x32_10_rk(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, const uint32_t* __restrict__ rk)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        uint32_t n0 = hi1 ^ c1 ^ rk[2 * r];
+        uint32_t n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+    }
+}
+
 // Call key = first two output words of Philox(key = seed, ctr = (offset, 'PGM1', 'key!')).
 __host__ __device__ inline PhiloxKey
 derive_call_key(uint64_t seed, uint64_t offset)
 {
     uint32_t c0 = (uint32_t)offset, c1 = (uint32_t)(offset >> 32), c2 = 0x50474D31u, c3 = 0x6B657921u;
     philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
-    return PhiloxKey{c0, c1};
+    PhiloxKey key;
+    key.k0 = c0;
+    key.k1 = c1;
+    philox_round_keys(key);
+    return key;
 }
 
 #ifdef __CUDACC__
@@ -248,16 +286,21 @@ philox_block_outlined(uint32_t i0, uint32_t i1, uint32_t blk, uint32_t k0, uint3
     return make_uint4(b0, b1, b2, b3);
 }
 
-template <bool OUTLINE>
+// RK (inline variant only): XOR the precomputed round keys of the kernel's parameter bank instead of
+// bumping the key per round -- pays in a dense kernel with one block per element (normal: -2.4 %),
+// costs in the persistent kernels, where the pointer has to be kept live (devroye: +2.5 %).
+template <bool OUTLINE, bool RK = false>
 struct RngT {
     uint32_t k0, k1, i0, i1, blk;
     uint32_t b0, b1, b2, b3;
     int left;
+    const uint32_t* rk;  // round keys in the kernel's parameter bank (inline variant)
 
-    __device__ __forceinline__ void init(PhiloxKey key, uint64_t index)
+    __device__ __forceinline__ void init(const PhiloxKey& key, uint64_t index)
     {
         k0 = key.k0;
         k1 = key.k1;
+        rk = RK ? key.rk : nullptr;
         i0 = (uint32_t)index;
         i1 = (uint32_t)(index >> 32);
         blk = 0;
@@ -280,7 +323,8 @@ struct RngT {
             b1 = i1;
             b2 = blk;
             b3 = 0;
-            philox4x32_10(b0, b1, b2, b3, k0, k1);
+            if (RK) philox4x32_10_rk(b0, b1, b2, b3, rk);
+            else philox4x32_10(b0, b1, b2, b3, k0, k1);
         }
         ++blk;
         left = 4;
@@ -431,6 +475,7 @@ log_upper_gamma(double p, double x, bool normalized)
 
 using RngOutlined = RngT<true>;
 using RngInline = RngT<false>;
+using RngInlineRK = RngT<false, true>;
 
 // random_left_bounded_gamma (src/pgm_common.h:126-157): X ~ Gamma(a, rate b) | X > t
 template <class R>

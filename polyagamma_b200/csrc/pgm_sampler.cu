@@ -532,7 +532,7 @@ dense_kernel(FillArgs a, Bucket b)
 #pragma unroll
             for (int i = 0; i < E; ++i) {
                 double bad;
-                RngInline r;
+                RngInlineRK r;
                 r.init(a.key, a.first_index + a.base + e[i]);
                 out[i] = invalid_h(h[i], bad) ? bad : normal_approx_sample(r, h[i], z[i]);
             }
