@@ -39,21 +39,21 @@ WORKLOAD = "cfg4: fill2 hybrid, h~U[0.1,200], z~U[-50,50] (BASELINE.json configs
 
 # FP64 flops per element of each kernel on the cfg4 distribution: executed thread-level
 # instructions 2*DFMA + DMUL + DADD (ncu smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on)
-# of one profiled launch divided by the elements of that launch -- profiles/r1g_cfg4_all_kernels.txt,
+# of one profiled launch divided by the elements of that launch -- profiles/r1i_cfg4_all_kernels.txt,
 # table in profiles/README.md (SURVEY 8(d)'s nominal per-method figures are kept beside them there).
 # devroye figures are from the cfg2 capture (cfg4 has no devroye elements).
-FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 596.0, "alternate_left": 383.0, "saddle": 602.0,
-                     "saddle_left": 642.0, "saddle_far": 298.0, "saddle_mid": 298.0, "normal": 150.0, "gamma": 6.0e4,
-                     "setup_devroye": 356.0, "setup_alternate": 1222.0, "setup_alternate_left": 1.0,
-                     "setup_saddle": 1790.0, "setup_saddle_left": 363.0, "setup_saddle_far": 269.0,
-                     "setup_saddle_mid": 269.0}
+FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 589.0, "alternate_left": 383.0, "saddle": 600.0,
+                     "saddle_left": 640.0, "saddle_far": 289.0, "saddle_mid": 357.0, "normal": 152.0, "gamma": 6.0e4,
+                     "setup_devroye": 356.0, "setup_alternate": 1209.0, "setup_alternate_left": 1.0,
+                     "setup_saddle": 1790.0, "setup_saddle_left": 362.0, "setup_saddle_far": 266.0,
+                     "setup_saddle_mid": 292.0}
 # DRAM bytes per element of each kernel: (dram__bytes_read.sum + dram__bytes_write.sum) of the same ncu
 # capture divided by the elements of that launch.  Algorithmic bytes are 28 (normal: list index + h + z +
 # out) to ~90 (record kernels); the sparse buckets pay 32-byte sectors for 8-byte gathers of h and z.
-DRAM_BYTES_PER_ELEMENT = {"normal": 42.1, "saddle_far": 82.0, "saddle_mid": 82.0, "saddle_left": 107.4,
-                          "saddle": 118.1, "alternate": 80.1, "alternate_left": 69.5, "setup_saddle_far": 116.9,
-                          "setup_saddle_mid": 116.9, "setup_saddle_left": 241.9, "setup_saddle": 259.2,
-                          "setup_alternate": 257.2, "setup_alternate_left": 231.8}
+DRAM_BYTES_PER_ELEMENT = {"normal": 42.0, "saddle_far": 83.0, "saddle_mid": 85.8, "saddle_left": 105.7,
+                          "saddle": 112.9, "alternate": 75.3, "alternate_left": 66.6, "setup_saddle_far": 127.8,
+                          "setup_saddle_mid": 234.6, "setup_saddle_left": 240.4, "setup_saddle": 258.0,
+                          "setup_alternate": 251.5, "setup_alternate_left": 233.7}
 KERNEL_NAMES = {"devroye": "sample_kernel<Devroye>", "alternate": "sample_kernel<Alternate>",
                 "alternate_left": "sample_kernel<AlternateLeft>", "setup_alternate_left": "setup_kernel<AlternateLeft>",
                 "saddle": "sample_kernel<SaddleFull>", "saddle_left": "sample_kernel<SaddleLeft>",
@@ -63,7 +63,7 @@ KERNEL_NAMES = {"devroye": "sample_kernel<Devroye>", "alternate": "sample_kernel
                 "setup_devroye": "setup_kernel<Devroye>", "setup_alternate": "setup_kernel<Alternate>",
                 "setup_saddle": "setup_kernel<SaddleFull>", "setup_saddle_left": "setup_kernel<SaddleLeft>",
                 "setup_saddle_far": "setup_kernel<SaddleFar>"}
-BYTES_PER_ELEMENT = 24 + 5  # h, z in + out (+ 1 B method id and 4 B list index written and read once)
+BYTES_PER_ELEMENT = 24 + 4  # h, z in + out + the 4-byte list index of the bucketing pass
 
 
 def parse_args():
@@ -340,7 +340,7 @@ def main():
         "flops_per_unit": FLOPS_PER_ELEMENT[dom], "units_per_launch": units_per_launch,
         "launch_ms": per_launch_s * 1e3, "share_of_step": dom_ms / total_kernel_ms if total_kernel_ms else None,
         "traffic": (units_per_launch * DRAM_BYTES_PER_ELEMENT[dom]) if dom in DRAM_BYTES_PER_ELEMENT else None,
-        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per element (profiles/r1g_cfg4_all_kernels.txt) "
+        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per element (profiles/r1i_cfg4_all_kernels.txt) "
                           "x elements of this launch",
         "timing": "per-kernel times: same K steps with the kernels serialised (PGM_CUDA_NO_OVERLAP=1); the timed "
                   "region itself overlaps the kernels of a pass on helper streams",
