@@ -46,7 +46,14 @@ using RngFor = RngT<((PGM_RNG_OUTLINE_MASK >> BIT) & 1) != 0>;
 // =========================================================================================
 // Devroye: exact J*(1, z), summed floor(h) times            (src/pgm_devroye.c)
 // =========================================================================================
-struct Devroye {
+// LEFT fixes the proposal of the truncated inverse-Gaussian piece at compile time: the hybrid
+// dispatch buckets devroye elements by |z|/2 < 1/T (exponential pairs) or not (Michael-Schucany-Haas)
+// so that the lanes of a warp do not serialise the two (cfg2, z ~ N(0, 3): 70 % / 30 %; 13.5 of 32
+// lanes active when mixed).  kDevroyeAny decides per element (explicit method on the identity range).
+enum : int { kDevroyeAny = 0, kDevroyePair = 1, kDevroyeMSH = 2 };
+
+template <int LEFT>
+struct DevroyeT {
     using Rng = RngFor<0>;
     static constexpr double T = 0.64;
     static constexpr int kFields = 4;  // w, K, zz, count
@@ -128,7 +135,8 @@ struct Devroye {
         const double L = -log(r.uniform_oc());
         if (left) {
             s.in_left = 1;
-            if (p.zz < 1.5625) {  // 1/T: exponential-pair proposal of Devroye (2009)
+            const bool pair = LEFT == kDevroyePair ? true : LEFT == kDevroyeMSH ? false : (p.zz < 1.5625);
+            if (pair) {  // |z|/2 < 1/T: exponential-pair proposal of Devroye (2009)
                 const double e2 = r.exponential();
                 if (L * L > 3.125 * e2) return false;
                 x = 1.0 + T * L;
@@ -185,6 +193,8 @@ struct Devroye {
         return false;
     }
 };
+
+using Devroye = DevroyeT<kDevroyeAny>;
 
 // =========================================================================================
 // Alternate: J*(h, z) for h <= 4, chunked above             (src/pgm_alternate.c)

@@ -147,16 +147,18 @@ constexpr uint8_t kBucketNone = 255;
 // bucket ids (also the order of the per-method lists inside the chunk's index list)
 // (the gamma method never needs the pre-pass: it runs on the identity range)
 enum : int { kBDevroye = 0, kBAlternate = 1, kBSaddleFull = 2, kBSaddleLeft = 3, kBSaddleFar = 4, kBAlternateLeft = 5,
-             kBSaddleMid = 6, kBNormal = 7, kNumBuckets = 8, kBGamma = 8 };
+             kBSaddleMid = 6, kBNormal = 7, kBDevroyeMSH = 8, kNumBuckets = 9, kBGamma = 9 };
 
-// ctl layout (uint32): [0..7] bucket counts, [8..15] record bases, [16..23] work counters, [24] ticket
-constexpr int kCtlCount = 0, kCtlBase = 8, kCtlWork = 16, kCtlTicket = 24, kCtlWords = 32;
+// ctl layout (uint32): [0..9] bucket counts, [10..19] record bases, [20..29] work counters, [30] ticket
+constexpr int kCtlCount = 0, kCtlBase = 10, kCtlWork = 20, kCtlTicket = 30, kCtlWords = 32;
+static_assert(kNumBuckets <= 10, "ctl layout");
 
 __host__ __device__ __forceinline__ int
 bucket_of(int method, double h, double z, bool compat)
 {
     switch (method) {
-        case kDevroye: return kBDevroye;
+        // |z|/2 < 1/T: exponential-pair proposal, else Michael-Schucany-Haas (z = NaN is sampled as z = 0)
+        case kDevroye: return (0.5 * fabs(z) >= 1.5625) ? kBDevroyeMSH : kBDevroye;
         case kAlternate: return alternate_left_only(z) ? kBAlternateLeft : kBAlternate;
         case kSaddle: {
             // the far kernel's buckets: |z| >= 14 (proposals below x = 0.2 almost surely: closed-form
@@ -209,9 +211,8 @@ __global__ void __launch_bounds__(kBucketThreads)
 bucket_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, uint32_t* __restrict__ list,
               uint32_t list_stride)
 {
-    static_assert(kNumBuckets <= 8 && kPacked == 4, "offsets are packed 4 x 16 bit into two 64-bit words");
     __shared__ uint32_t s_cnt[kPacked];
-    __shared__ uint32_t s_run[8];  // next free list slot of each bucket for this block
+    __shared__ uint32_t s_run[kNumBuckets];  // next free list slot of each bucket for this block
     __shared__ __align__(8) uint8_t s_meth[kTilesPerBlock][kBucketTile];
     const uint32_t lane = threadIdx.x & 31;
     if (threadIdx.x < kPacked) s_cnt[threadIdx.x] = 0;
@@ -766,7 +767,8 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
             a.base = base0 + off;
             Bucket b{nullptr, nullptr, bk, cn, 0, params, 1};
             switch (bk) {
-                case kBDevroye: launch_method<Devroye>(d, 0, a, b, cn, counters + c, s); break;
+                case kBDevroye: launch_method<DevroyeT<kDevroyePair>>(d, 0, a, b, cn, counters + c, s); break;
+                case kBDevroyeMSH: launch_method<DevroyeT<kDevroyeMSH>>(d, 0, a, b, cn, counters + c, s); break;
                 case kBAlternate: launch_method<Alternate>(d, 1, a, b, cn, counters + c, s); break;
                 case kBSaddleFull: launch_method<SaddleFull>(d, 2, a, b, cn, counters + c, s); break;
                 case kBSaddleLeft: launch_method<SaddleLeft>(d, 3, a, b, cn, counters + c, s); break;
@@ -876,7 +878,8 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
                                          m == kAlternate ? s : s1);
         }
         if (m == kHybrid) {
-            launch_method<Devroye>(d, 0, ap, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s2);
+            launch_method<DevroyeT<kDevroyePair>>(d, 0, ap, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s2);
+            launch_method<DevroyeT<kDevroyeMSH>>(d, 0, ap, bucket(kBDevroyeMSH), cn, ctl + kCtlWork + kBDevroyeMSH, s1);
             launch_dense<kNormal>(d, ap, bucket(kBNormal), cn, s);
         }
     };
