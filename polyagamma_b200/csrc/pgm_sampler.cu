@@ -617,7 +617,7 @@ device_info()
     DeviceInfo& d = cache[dev & 63];
     if (d.sms == 0) {
         cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[0], sample_kernel<Devroye>, kPersistThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[0], sample_kernel<DevroyeT<kDevroyePair>>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[1], sample_kernel<Alternate>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[2], sample_kernel<SaddleFull>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[3], sample_kernel<SaddleLeft>, kPersistThreads, 0);
@@ -783,9 +783,9 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         return (int)cudaGetLastError();
     }
 
-    // per-element parameters (fill2).  hybrid, saddle and alternate need the bucketing pre-pass
-    // (they split into specialised kernels); devroye and gamma run on the identity range.
-    const bool bucketed = (m == kHybrid || m == kSaddle || m == kAlternate);
+    // per-element parameters (fill2).  hybrid, saddle, alternate and devroye go through the bucketing
+    // pre-pass (they split into specialised kernels); gamma runs on the identity range.
+    const bool bucketed = (m == kHybrid || m == kSaddle || m == kAlternate || m == kDevroye);
     int lg = first_chunk_log2(n);
     // With several passes the bucketing of pass k+1 (HBM- and issue-bound) runs on a helper stream
     // while the sampling kernels of pass k (FP64-bound) run on the caller's stream; the bucketing
@@ -837,10 +837,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
             a.base = base0 + off;
             cudaMemsetAsync(ctl, 0, ctl_bytes, s);
             Bucket b{nullptr, nullptr, 0, cn, 0, params, 0};
-            switch (m) {
-                case kDevroye: launch_method<Devroye>(d, 0, a, b, cn, ctl + kCtlWork, s); break;
-                default: launch_dense<kGamma>(d, a, b, cn, s); break;
-            }
+            launch_dense<kGamma>(d, a, b, cn, s);
         }
         cudaFreeAsync(ws, s);
         return (int)cudaGetLastError();
@@ -866,22 +863,23 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     auto sampling = [&](const FillArgs& ap, uint32_t cn, const Prep& pp, cudaStream_t s1, cudaStream_t s2) {
         uint32_t* ctl = pp.ctl;
         auto bucket = [&](int q) { return Bucket{pp.list, ctl, q, 0, list_stride, params, 0}; };
-        if (m != kAlternate) {
+        if (m == kHybrid || m == kSaddle) {
             launch_method<SaddleFar>(d, 4, ap, bucket(kBSaddleFar), cn, ctl + kCtlWork + kBSaddleFar, s);
             launch_method<SaddleFar>(d, 6, ap, bucket(kBSaddleMid), cn, ctl + kCtlWork + kBSaddleMid, s1);
             launch_method<SaddleLeft>(d, 3, ap, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s1);
             launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s2);
         }
-        if (m != kSaddle) {
+        if (m == kHybrid || m == kAlternate) {
             launch_method<Alternate>(d, 1, ap, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s2);
             launch_method<AlternateLeft>(d, 5, ap, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft,
                                          m == kAlternate ? s : s1);
         }
-        if (m == kHybrid) {
+        if (m == kHybrid || m == kDevroye) {
             launch_method<DevroyeT<kDevroyePair>>(d, 0, ap, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s2);
-            launch_method<DevroyeT<kDevroyeMSH>>(d, 0, ap, bucket(kBDevroyeMSH), cn, ctl + kCtlWork + kBDevroyeMSH, s1);
-            launch_dense<kNormal>(d, ap, bucket(kBNormal), cn, s);
+            launch_method<DevroyeT<kDevroyeMSH>>(d, 0, ap, bucket(kBDevroyeMSH), cn, ctl + kCtlWork + kBDevroyeMSH,
+                                                 m == kDevroye ? s : s1);
         }
+        if (m == kHybrid) launch_dense<kNormal>(d, ap, bucket(kBNormal), cn, s);
     };
 
     const bool multi = cmax_elems >= (1ull << 20) && getenv("PGM_CUDA_NO_OVERLAP") == nullptr;
