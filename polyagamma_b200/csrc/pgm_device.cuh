@@ -424,11 +424,11 @@ confluent_x_smaller(double p, double x)
     for (int n = 2; n < kLentzMaxIt; ++n) {
         a = (n & 1) ? s * (n - 1) : r - s * n;
         b += 1.0;
-        c = b + a / c;
+        c = b + a * fm::rcp(c);  // |c|, |d| >= 1e-290: normal numbers, the MUFU-seeded reciprocal applies
         if (fabs(c) < kLentzTiny) c = kLentzTiny;
         d = a * d + b;
         if (fabs(d) < kLentzTiny) d = kLentzTiny;
-        d = 1.0 / d;
+        d = fm::rcp(d);
         double delta = c * d;
         f *= delta;
         if (fabs(delta - 1.0) < kLentzEps) break;
@@ -445,11 +445,11 @@ confluent_p_smaller(double p, double x)
     for (int n = 1; n < kLentzMaxIt; ++n) {
         a = n * (p - n);
         b += 2.0;
-        c = b + a / c;
+        c = b + a * fm::rcp(c);
         if (fabs(c) < kLentzTiny) c = kLentzTiny;
         d = a * d + b;
         if (fabs(d) < kLentzTiny) d = kLentzTiny;
-        d = 1.0 / d;
+        d = fm::rcp(d);
         double delta = c * d;
         f *= delta;
         if (fabs(delta - 1.0) < kLentzEps) break;

@@ -672,11 +672,11 @@ table_interp(const double* tab, double zz)
 __device__ __forceinline__ double
 invgauss_logcdf(double x, double mu, double lambda)
 {
-    double qm = x / mu;
-    double tm = mu / lambda;
-    double rr = sqrt(x / lambda);
-    double a = log_ndtr((qm - 1.0) / rr);
-    double b = 2.0 / tm + log_ndtr(-(qm + 1.0) / rr);
+    // (x, mu, lambda are positive normal numbers here: MUFU-seeded reciprocals)
+    double qm = fm::div(x, mu);
+    double rr_inv = fm::rsqrt(fm::div(x, lambda));
+    double a = log_ndtr((qm - 1.0) * rr_inv);
+    double b = 2.0 * fm::div(lambda, mu) + log_ndtr(-(qm + 1.0) * rr_inv);
     return a + log1p(exp(b - a));
 }
 
@@ -722,9 +722,11 @@ struct SaddleT {
         double zz = 0.5 * fabs(z);
         if (!(zz > 0.0)) zz = 0.0;
         double xl, half_z2, log_cosh_z;
-        if (zz > 0.0) {
+        // (below 1e-100 every quantity here equals its z = 0 value in double precision; the cut keeps
+        // the MUFU-seeded reciprocals on normal numbers)
+        if (zz > 1e-100) {
             const double e = exp(-2.0 * zz);
-            xl = (1.0 - e) / ((1.0 + e) * zz);  // tanh(zz) / zz
+            xl = fm::div(1.0 - e, (1.0 + e) * zz);  // tanh(zz) / zz
             half_z2 = 0.5 * zz * zz;
             // log cosh(zz) = zz - log 2 + log1p(e^{-2 zz})
             log_cosh_z = zz - kLog2 + (e < 2.5e-3 ? e * (1.0 - e * (0.5 - e * (1.0 / 3.0 - 0.25 * e))) : log1p(e));
@@ -735,7 +737,7 @@ struct SaddleT {
             log_cosh_z = 0.0;
         }
         const double xc = 2.75 * xl;
-        const double xc_inv = 1.0 / xc;
+        const double xc_inv = fm::rcp(xc);
         const double xl_inv = 2.75 * xc_inv;
         double f, fp_c;
         const bool tabulated = zz < kGuessZMax;
@@ -757,12 +759,12 @@ struct SaddleT {
                 kprime3(-half_z2, f_l, fp_l, fpp_l);
             }
             else {
-                const double inv = -1.0 / (zz * zz);
+                const double inv = -fm::rcp(zz * zz);
                 const double t = (1.0 - xl) * inv;
                 fp_l = xl * xl + t;
                 fpp_l = 2.0 * xl * fp_l - fp_l * inv - 2.0 * t * inv;
             }
-            const double a1 = 1.0 / fp_l;
+            const double a1 = fm::rcp(fp_l);
             rec[4] = a1;
             rec[5] = -0.5 * fpp_l * a1 * a1 * a1;
         }
@@ -773,7 +775,7 @@ struct SaddleT {
             double ur = solve(xr, tabulated ? table_interp(g_guess_ur, zz) : table_guess(xr), f, fp_r);
             const double tr = ur + half_z2;
             const double logxc = 1.0116009116784799 + logxl;  // log(2.75)
-            const double slope_r = -tr - 1.0 / xr;
+            const double slope_r = -tr - fm::rcp(xr);
             const double icpt_r = (log_cosh_z + cumulant0(ur, f)) + 1.0 - 1.0986122886681098 - logxl + logxc;
             const double log_sqrt_h2pi = 0.5 * log(h / (2.0 * kPi));
             const double log_coef_r = log_sqrt_h2pi - 0.5 * log(alpha_r);
