@@ -487,33 +487,37 @@ left_bounded_gamma(R& r, double a, double b, double t)
         b = t * b;
         double amin1 = a - 1.0;
         double bmina = b - a;
-        double c0 = 0.5 * (bmina + sqrt(bmina * bmina + 4.0 * b)) / b;
+        // (a, b, t are positive normal numbers: divisions by MUFU-seeded reciprocals, hoisted out of
+        // the rejection loops)
+        const double inv_b = fm::rcp(b);
+        double c0 = 0.5 * (bmina + sqrt(bmina * bmina + 4.0 * b)) * inv_b;
         double one_minus_c0 = 1.0 - c0;
-        double log_m = amin1 * (log(amin1 / one_minus_c0) - 1.0);
+        double log_m = amin1 * (log(fm::div(amin1, one_minus_c0)) - 1.0);
+        const double inv_c0 = fm::rcp(c0);
         double threshold;
         do {
-            x = b + r.exponential() / c0;
+            x = b + r.exponential() * inv_c0;
             threshold = amin1 * log(x) - x * one_minus_c0 - log_m;
         } while (log(r.uniform32()) > threshold);
-        return t * (x / b);
+        return t * (x * inv_b);
     }
     else if (a == 1.0) {
-        return t + r.exponential() / b;
+        return t + r.exponential() * fm::rcp(b);
     }
     else if (a == 0.5) {  // Philippe (1997) A4; u < x^(-1/2) written as u^2 x < 1
-        double tb = t * b;
+        const double inv_tb = fm::rcp(t * b);
         double u;
         do {
-            x = 1.0 + r.exponential() / tb;
+            x = 1.0 + r.exponential() * inv_tb;
             u = r.uniform32();
         } while (u * u * x > 1.0);
         return t * x;
     }
     else {
         double amin1 = a - 1.0;
-        double tb = t * b;
+        const double inv_tb = fm::rcp(t * b);
         do {
-            x = 1.0 + r.exponential() / tb;
+            x = 1.0 + r.exponential() * inv_tb;
         } while (log(r.uniform32()) > amin1 * log(x));
         return t * x;
     }

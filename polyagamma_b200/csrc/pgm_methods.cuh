@@ -85,8 +85,9 @@ struct DevroyeT {
             double t2 = (a + b < 26.5) ? erfc(a + b) * exp(zz) : 0.0;
             double pp = t1 + t2;
             K = kPi2_8 + 0.5 * zz * zz;
-            double q = kPi_2 * exp(-K * T) / K;
-            w = (pp + q > 0.0) ? pp / (pp + q) : 1.0;
+            double q = kPi_2 * exp(-K * T) * fm::rcp(K);
+            // (the sum underflows only for |z| far beyond any finite-variance use: IEEE division there)
+            w = (pp + q > 1e-290) ? fm::div(pp, pp + q) : (pp + q > 0.0) ? pp / (pp + q) : 1.0;
         }
         else {
             w = 0.4223027567786595;  // src/pgm_devroye.c:78
@@ -215,7 +216,7 @@ struct Alternate {
 
     struct Par {
         double w_right;  // q / (p + q): probability of the truncated-gamma (right) piece
-        double h, zz, z2, t, t_inv, lambda, half_h2, lgammah, hlog2, h_z, h_z2, ca;
+        double h, zz, z2, t, t_inv, lambda, half_h2, lgammah, hlog2, h_z, h_z2, ca, inv_z2, logh;
     };
     struct State {
         double acc;
@@ -243,7 +244,7 @@ struct Alternate {
         lgammah = pgm_lgamma(h);
         double hlog2 = h * kLog2;
         double lp, lambda;
-        double a = h / sqrt(2.0 * t);
+        double a = h * fm::rsqrt(2.0 * t);
         if (zz > 0.0) {
             lambda = kPi2_8 + 0.5 * zz * zz;
             double b = zz * sqrt(0.5 * t);
@@ -291,17 +292,21 @@ struct Alternate {
         p.h = h;
         p.zz = zz;
         p.t = trunc_point(h);
-        p.t_inv = 1.0 / p.t;
+        p.t_inv = fm::rcp(p.t);
         p.half_h2 = 0.5 * h * h;
         p.hlog2 = h * kLog2;
+        p.logh = log(h);
         p.ca = compat ? 0.5 * kLogPi_2 : kLogPi_2;  // src/pgm_alternate.c:90
         p.z2 = zz * zz;
         p.lambda = kPi2_8 + 0.5 * p.z2;
-        if (zz > 0.0) {
-            p.h_z = h / zz;
+        if (zz > 1e-100) {  // (below: h / zz is "infinite" for every test it enters, as in the oracle)
+            const double inv_z = fm::rcp(zz);
+            p.inv_z2 = inv_z * inv_z;
+            p.h_z = h * inv_z;
             p.h_z2 = p.h_z * p.h_z;
         }
         else {
+            p.inv_z2 = INFINITY;
             p.h_z = INFINITY;
             p.h_z2 = INFINITY;
         }
@@ -331,7 +336,7 @@ struct Alternate {
 
     static __device__ __forceinline__ double inv_left_gamma(const Par& p, Rng& r)
     {
-        return 1.0 / left_bounded_gamma(r, 0.5, p.half_h2, p.t_inv);
+        return fm::rcp(left_bounded_gamma(r, 0.5, p.half_h2, p.t_inv));
     }
 
     // random_right_bounded_invgauss (src/pgm_alternate.c:200-218)
@@ -346,10 +351,10 @@ struct Alternate {
         }
         do {
             double y = r.normal();
-            double w = p.h_z + 0.5 * y * y / p.z2;
-            x = p.h_z2 / (w + sqrt(fmax(w * w - p.h_z2, 0.0)));
+            double w = p.h_z + 0.5 * y * y * p.inv_z2;
+            x = p.h_z2 * fm::rcp(w + sqrt(fmax(w * w - p.h_z2, 0.0)));
             if (r.uniform_co() * (p.h_z + x) > p.h_z) {
-                x = p.h_z2 / x;
+                x = p.h_z2 * fm::rcp(x);
             }
         } while (x >= p.t);
         return x;
@@ -369,24 +374,25 @@ struct Alternate {
             x = inv_left_gamma(p, r);
         }
         double logx = log(x);
+        const double rx = fm::rcp(x);
         double lk;
         if (x > p.t) {  // bounding_kernel (src/pgm_alternate.c:86-99)
             lk = p.h * p.ca + (p.h - 1.0) * logx - kPi2_8 * x - p.lgammah;
         }
         else {
-            lk = p.hlog2 - p.half_h2 / x - 1.5 * logx - kLs2Pi + log(p.h);
+            lk = p.hlog2 - p.half_h2 * rx - 1.5 * logx - kLs2Pi + p.logh;
         }
         double u = r.uniform32() * exp(lk);
         // piecewise_coef (src/pgm_alternate.c:75-83) with c_n = c_{n-1} (n - 1 + h) / n
         double base = p.hlog2 - kLs2Pi - 1.5 * logx;
-        double inv2x = 0.5 / x;
+        double inv2x = 0.5 * rx;
         double c = 1.0;
         double a_prev = p.h * exp(base - p.h * p.h * inv2x);
         double sum = a_prev;
         bool accept = false;
         for (int n = 1; n < 2000; ++n) {
             double tn = 2.0 * n + p.h;
-            c *= (n - 1.0 + p.h) / n;
+            c *= fm::div(n - 1.0 + p.h, (double)n);
             double a = c * tn * exp(base - tn * tn * inv2x);
             if (n & 1) {
                 sum -= a;
