@@ -982,7 +982,10 @@ gamma_conv_sample(GammaRng& r, double h, double z)
                     v = v * v * v;
                     const double u = r.uniform_oc();
                     const double x2 = x * x;
-                    if (u < 1.0 - 0.0331 * x2 * x2 || log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) {
+                    // Marsaglia-Tsang's squeeze u < 1 - 0.0331 x^4 only implies the test below; in a warp
+                    // some lane fails it on 93 % of the attempts, so the two logarithms are paid for
+                    // anyway -- evaluating them for every lane keeps the warp converged.
+                    if (log(u) < 0.5 * x2 + d * (1.0 - v + log(v))) {
                         double g = d * v;
                         if (boost) g *= exp(log(r.uniform_oc()) * inv_h);
                         const double m = k + 0.5;
