@@ -658,7 +658,7 @@ solve(double x, double u, double& f, double& fp)
 // 1/16, filled once per device by init_guess_tables_kernel with the solver itself) and
 // interpolated linearly -- error ~1e-4, so one Halley step lands below the 1e-9 tolerance and
 // every lane of a warp takes the same two evaluations.
-constexpr double kGuessZMax = 11.0;
+constexpr double kGuessZMax = 26.0;
 constexpr int kGuessPerUnit = 16;
 constexpr int kGuessN = (int)(kGuessZMax * kGuessPerUnit) + 2;
 static __device__ double g_guess_uc[kGuessN];
