@@ -422,7 +422,16 @@ setup_kernel(FillArgs a, Bucket b)
 constexpr int kPersistThreads = 256;
 constexpr uint32_t kWorkBatch = 64;  // elements a warp reserves per atomic
 
-template <class M>
+// FUSED: the lane computes its element's record itself at refill (registers only) instead of reading
+// what setup_kernel stored -- for a method whose setup is short and whose lanes all refill on nearly
+// every trip (saddle-far: 1.004 proposals per sample), this saves the record's round trip through
+// HBM and the second gather of (h, z).
+struct LocalRec {
+    const double* v;
+    __device__ __forceinline__ double operator[](int f) const { return v[f]; }
+};
+
+template <class M, bool FUSED = false>
 __global__ void __launch_bounds__(kPersistThreads)
 sample_kernel(FillArgs a, Bucket b, uint32_t* __restrict__ counter)
 {
@@ -460,15 +469,29 @@ sample_kernel(FillArgs a, Bucket b, uint32_t* __restrict__ counter)
                 if (!active && pos < wend) {
                     uint32_t e = v.list ? v.list[pos] : pos;
                     g = a.base + e;
-                    RecView rec{v.recs, v.stride, b.uniform ? 0u : pos};
-                    double r0 = rec[0];
-                    if (r0 == r0) {  // NaN record: invalid h, already written by setup_kernel
-                        if (M::load(rec, par, st, compat)) {
+                    if (FUSED) {  // (bucketed lists only: invalid h never reaches a list)
+                        double h, z, loc[M::kFields];
+                        load_hz(a, g, h, z);
+                        M::make_record(h, z, compat, loc);
+                        if (M::load(LocalRec{loc}, par, st, compat)) {
                             rng.init(a.key, a.first_index + g);
                             active = true;
                         }
                         else {
-                            a.out[g] = 0.0;  // nothing to draw (devroye with floor(h) == 0)
+                            a.out[g] = 0.0;
+                        }
+                    }
+                    else {
+                        RecView rec{v.recs, v.stride, b.uniform ? 0u : pos};
+                        double r0 = rec[0];
+                        if (r0 == r0) {  // NaN record: invalid h, already written by setup_kernel
+                            if (M::load(rec, par, st, compat)) {
+                                rng.init(a.key, a.first_index + g);
+                                active = true;
+                            }
+                            else {
+                                a.out[g] = 0.0;  // nothing to draw (devroye with floor(h) == 0)
+                            }
                         }
                     }
                 }
@@ -668,23 +691,30 @@ grid_for(uint64_t full, uint64_t count_hint, uint32_t threads)
 // setup + persistent sampling of one bucket with method M (which: 0 devroye, 1 alternate,
 // 2 saddle-full, 3 saddle-left, 4 saddle-far, 5 alternate-left, 6 saddle-mid; profiling kinds are
 // kKindDevroye / kKindSetup + which)
-template <class M>
+// Which buckets compute their records inside the sampling kernel (measured on cfg4, ms per 1e9,
+// setup + sampling separate -> fused): saddle-far 8.25 -> 6.86, saddle-mid 2.71 -> 2.44, alternate-left
+// 2.04 -> 1.55; saddle-left gets slower (3.83 -> 4.22: its setup is longer and its lanes refill out
+// of step), and the full saddle / alternate setups are the big ones the split exists for.
+constexpr bool kFuseFar = true, kFuseMid = true, kFuseLeft = false, kFuseAltLeft = true;
+constexpr bool kFuseDevroye = false;  // cfg2: 13.9 -> 12.5e9 samples/s when fused (two erfc in the refill)
+
+template <class M, bool FUSED = false>
 static void
 launch_method(const DeviceInfo& d, int which, const FillArgs& a, const Bucket& b, uint64_t count_hint,
               uint32_t* counter, cudaStream_t s)
 {
     const int kind = kKindDevroye + which;
-    {
+    if (!FUSED) {
         ScopedKernelTimer timer(kKindSetup + which, s);
         uint64_t nrec = b.uniform ? 1 : count_hint;
         setup_kernel<M><<<grid_for((uint64_t)d.sms * 8, nrec, 256), 256, 0, s>>>(a, b);
     }
     {
         ScopedKernelTimer timer(kind, s);
-        sample_kernel<M><<<grid_for((uint64_t)d.sms * d.blocks_per_sm[which], count_hint, kPersistThreads),
-                           kPersistThreads, 0, s>>>(a, b, counter);
+        sample_kernel<M, FUSED><<<grid_for((uint64_t)d.sms * d.blocks_per_sm[which], count_hint, kPersistThreads),
+                                  kPersistThreads, 0, s>>>(a, b, counter);
     }
-    count_launch(2);
+    count_launch(FUSED ? 1 : 2);
 }
 
 template <int KIND>
@@ -864,19 +894,19 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         uint32_t* ctl = pp.ctl;
         auto bucket = [&](int q) { return Bucket{pp.list, ctl, q, 0, list_stride, params, 0}; };
         if (m == kHybrid || m == kSaddle) {
-            launch_method<SaddleFar>(d, 4, ap, bucket(kBSaddleFar), cn, ctl + kCtlWork + kBSaddleFar, s);
-            launch_method<SaddleFar>(d, 6, ap, bucket(kBSaddleMid), cn, ctl + kCtlWork + kBSaddleMid, s1);
-            launch_method<SaddleLeft>(d, 3, ap, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s1);
+            launch_method<SaddleFar, kFuseFar>(d, 4, ap, bucket(kBSaddleFar), cn, ctl + kCtlWork + kBSaddleFar, s);
+            launch_method<SaddleFar, kFuseMid>(d, 6, ap, bucket(kBSaddleMid), cn, ctl + kCtlWork + kBSaddleMid, s1);
+            launch_method<SaddleLeft, kFuseLeft>(d, 3, ap, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s1);
             launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s2);
         }
         if (m == kHybrid || m == kAlternate) {
             launch_method<Alternate>(d, 1, ap, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s2);
-            launch_method<AlternateLeft>(d, 5, ap, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft,
+            launch_method<AlternateLeft, kFuseAltLeft>(d, 5, ap, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft,
                                          m == kAlternate ? s : s1);
         }
         if (m == kHybrid || m == kDevroye) {
-            launch_method<DevroyeT<kDevroyePair>>(d, 0, ap, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s2);
-            launch_method<DevroyeT<kDevroyeMSH>>(d, 0, ap, bucket(kBDevroyeMSH), cn, ctl + kCtlWork + kBDevroyeMSH,
+            launch_method<DevroyeT<kDevroyePair>, kFuseDevroye>(d, 0, ap, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s2);
+            launch_method<DevroyeT<kDevroyeMSH>, kFuseDevroye>(d, 0, ap, bucket(kBDevroyeMSH), cn, ctl + kCtlWork + kBDevroyeMSH,
                                                  m == kDevroye ? s : s1);
         }
         if (m == kHybrid) launch_dense<kNormal>(d, ap, bucket(kBNormal), cn, s);
