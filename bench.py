@@ -39,25 +39,26 @@ WORKLOAD = "cfg4: fill2 hybrid, h~U[0.1,200], z~U[-50,50] (BASELINE.json configs
 
 # FP64 flops per element of each kernel on the cfg4 distribution: executed thread-level
 # instructions 2*DFMA + DMUL + DADD (ncu smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on)
-# of one profiled launch divided by the elements of that launch -- profiles/r1i_cfg4_all_kernels.txt,
+# of one profiled launch divided by the elements of that launch -- profiles/r1j_cfg4_all_kernels.txt,
 # table in profiles/README.md (SURVEY 8(d)'s nominal per-method figures are kept beside them there).
 # devroye figures are from the cfg2 capture (cfg4 has no devroye elements).
-FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 589.0, "alternate_left": 383.0, "saddle": 600.0,
-                     "saddle_left": 640.0, "saddle_far": 289.0, "saddle_mid": 357.0, "normal": 152.0, "gamma": 6.0e4,
-                     "setup_devroye": 356.0, "setup_alternate": 1209.0, "setup_alternate_left": 1.0,
-                     "setup_saddle": 1790.0, "setup_saddle_left": 362.0, "setup_saddle_far": 266.0,
-                     "setup_saddle_mid": 292.0}
+FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 508.0, "alternate_left": 384.0, "saddle": 600.0,
+                     "saddle_left": 640.0, "saddle_far": 577.0, "saddle_mid": 645.0, "normal": 152.0, "gamma": 6.0e4,
+                     "setup_devroye": 356.0, "setup_alternate": 1091.0, "setup_saddle": 1654.0,
+                     "setup_saddle_left": 354.0,
+                     # the far / mid saddle and alternate-left buckets compute their records inside the
+                     # sampling kernel: no setup launch, the sampling figure includes the setup
+                     "setup_alternate_left": 0.0, "setup_saddle_far": 0.0, "setup_saddle_mid": 0.0}
 # DRAM bytes per element of each kernel: (dram__bytes_read.sum + dram__bytes_write.sum) of the same ncu
 # capture divided by the elements of that launch.  Algorithmic bytes are 28 (normal: list index + h + z +
 # out) to ~90 (record kernels); the sparse buckets pay 32-byte sectors for 8-byte gathers of h and z.
-DRAM_BYTES_PER_ELEMENT = {"normal": 42.0, "saddle_far": 83.0, "saddle_mid": 85.8, "saddle_left": 105.7,
-                          "saddle": 112.9, "alternate": 75.3, "alternate_left": 66.6, "setup_saddle_far": 127.8,
-                          "setup_saddle_mid": 234.6, "setup_saddle_left": 240.4, "setup_saddle": 258.0,
-                          "setup_alternate": 251.5, "setup_alternate_left": 233.7}
+DRAM_BYTES_PER_ELEMENT = {"normal": 42.0, "saddle_far": 146.9, "saddle_mid": 270.6, "saddle_left": 104.3,
+                          "saddle": 115.8, "alternate": 75.3, "alternate_left": 275.6,
+                          "setup_saddle_left": 241.2, "setup_saddle": 256.4, "setup_alternate": 253.8}
 KERNEL_NAMES = {"devroye": "sample_kernel<Devroye>", "alternate": "sample_kernel<Alternate>",
-                "alternate_left": "sample_kernel<AlternateLeft>", "setup_alternate_left": "setup_kernel<AlternateLeft>",
+                "alternate_left": "sample_kernel<AlternateLeft, fused setup>", "setup_alternate_left": "setup_kernel<AlternateLeft>",
                 "saddle": "sample_kernel<SaddleFull>", "saddle_left": "sample_kernel<SaddleLeft>",
-                "saddle_far": "sample_kernel<SaddleFar>", "saddle_mid": "sample_kernel<SaddleFar> (8<=|z|<14)",
+                "saddle_far": "sample_kernel<SaddleFar, fused setup>", "saddle_mid": "sample_kernel<SaddleFar, fused setup> (8<=|z|<14)",
                 "setup_saddle_mid": "setup_kernel<SaddleFar> (8<=|z|<14)",
                 "normal": "dense_kernel<normal>", "gamma": "dense_kernel<gamma>",
                 "setup_devroye": "setup_kernel<Devroye>", "setup_alternate": "setup_kernel<Alternate>",
@@ -331,7 +332,7 @@ def main():
     units_per_launch = units[dom] * args.steps / max(dom_launches, 1)
     achieved = units_per_launch * FLOPS_PER_ELEMENT[dom] / per_launch_s / 1e12
     total_kernel_ms = sum(v[0] for v in kernels.values())
-    step_flops = sum(units[k] * FLOPS_PER_ELEMENT[k] for k in units)
+    step_flops = sum(units[k] * FLOPS_PER_ELEMENT[k] for k in units if kernels[k][1])
     aggregate_tflops = step_flops * args.steps / (elapsed_ms * 1e-3) / 1e12
     roofline = {
         "bound": "fp64", "kernel": KERNEL_NAMES[dom],
@@ -340,7 +341,7 @@ def main():
         "flops_per_unit": FLOPS_PER_ELEMENT[dom], "units_per_launch": units_per_launch,
         "launch_ms": per_launch_s * 1e3, "share_of_step": dom_ms / total_kernel_ms if total_kernel_ms else None,
         "traffic": (units_per_launch * DRAM_BYTES_PER_ELEMENT[dom]) if dom in DRAM_BYTES_PER_ELEMENT else None,
-        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per element (profiles/r1i_cfg4_all_kernels.txt) "
+        "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per element (profiles/r1j_cfg4_all_kernels.txt) "
                           "x elements of this launch",
         "timing": "per-kernel times: same K steps with the kernels serialised (PGM_CUDA_NO_OVERLAP=1); the timed "
                   "region itself overlaps the kernels of a pass on helper streams",
