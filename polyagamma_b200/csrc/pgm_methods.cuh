@@ -257,7 +257,7 @@ struct Alternate {
             lambda = kPi2_8;
             lp = hlog2 + log(erfc(a));
         }
-        double lq = h * (kLogPi_2 - log(lambda)) + log_upper_gamma(h, lambda * t, true);
+        double lq = h * (kLogPi_2 - log(lambda)) + log_upper_gamma(h, lambda * t, true, lgammah);
         w_right = 1.0 / (1.0 + exp(lp - lq));
         if (!(w_right >= 0.0)) w_right = 0.0;
     }

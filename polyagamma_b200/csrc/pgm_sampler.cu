@@ -1041,6 +1041,7 @@ test_math_kernel(int which, const double* __restrict__ in, size_t n, double* __r
             case 5: y = fm::rsqrt(x); break;
             case 6: fm::sincos2pi(x, y, t); break;
             case 7: fm::sincos2pi(x, t, y); break;
+            case 9: y = pgm_lgamma(x); break;
             default: y = fm::div(1.0, x); break;
         }
         out[i] = y;

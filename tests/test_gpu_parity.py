@@ -329,6 +329,13 @@ def test_fast_math(torch):
     u = np.concatenate([rng.random(n), np.array([0.0, 0.25, 0.5, 0.75, 1.0, 0.125, 1 - 2.0**-53])])
     for which, ref in ((4, np.cos), (7, np.cos), (6, np.sin)):
         assert float(np.max(np.abs(run(which, u) - ref(2 * np.pi * u)))) <= 1e-15
+    # log Gamma (single-path Stirling form; integers 1..200 come from the reference's table)
+    from scipy.special import gammaln
+
+    xs = np.concatenate([rng.uniform(0.001, 30, n), 10.0 ** rng.uniform(-10, 6, n // 4),
+                         np.arange(1.0, 201.0), np.array([0.5, 1.5, 6.999999, 7.0, 7.000001, 201.0, 1e-300])])
+    got, want = run(9, xs), gammaln(xs)
+    assert float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want)))) <= 2e-14
     # special arguments fall back to libdevice semantics
     sp = np.array([0.0, np.inf, np.nan, -1.0, 5e-324])
     with np.errstate(all="ignore"):
