@@ -151,7 +151,7 @@ int pgm_cuda_fp64_peak_tflops(double* tflops, void* stream);
  * cached blocks of the current device to the driver (synchronises the device). */
 int pgm_cuda_release_scratch(void);
 /* Unit-test hook: applies one of the kernels' own elementary functions (csrc/pgm_device.cuh, fm::)
- * elementwise.  which: 0 rcp, 1 sqrt, 2 log, 3 exp, 4 cos(2 pi x), 5 rsqrt, 9 log Gamma, 6 sin(2 pi x) and
+ * elementwise.  which: 0 rcp, 1 sqrt, 2 log, 3 exp, 4 cos(2 pi x), 5 rsqrt, 9 log Gamma, 10 erfcx (x >= 0), 11 erfc (x >= 0), 6 sin(2 pi x) and
  * 7 cos(2 pi x) of the paired routine, 8 1/x by fm::div. */
 int pgm_cuda_test_math(int which, const double* d_in, size_t n, double* d_out, void* stream);
 /* "polyagamma_b200 <version> sm_100a" */

@@ -149,7 +149,7 @@ piece_logcdf(bool ig, double a, double s2x, double x, double z)
 //   z > 0:  F = Phi(A) + e^{z a} Phi(-B),  A = z sqrt(x) - a / (2 sqrt(x)),  B = z sqrt(x) + a / (2 sqrt(x))
 //             = 1/2 erfc(-A / sqrt 2) + 1/2 erfcx(B / sqrt 2) e^{-A^2 / 2}        (z a - B^2/2 = -A^2/2)
 //   z = 0:  F = erfc(a / (2 sqrt(2x)))
-// One erfc, one erfcx and one exp, no branch, instead of two (erf|erfc) + two log + log1p + exp
+// Two single-path erfcx and one exp, no branch, instead of two (erf|erfc) + two log + log1p + exp
 // behind four data-dependent branches.  Returns false where the reference switches to the Bryc
 // (A < -37.5 or B > 37.5, src/pgm_density.c:184-194) or A&S 7.1.28 (:154-163) forms: the caller
 // then takes the log-space path, which reproduces them.
@@ -160,12 +160,19 @@ piece_cdf_fast(bool ig, double a, double sx, double half_rsx, double zsx, double
         const double t = a * half_rsx;  // a / (2 sqrt(x))
         const double A = zsx - t, B = zsx + t;
         if (A < -37.5 || B > 37.5) return false;
-        F = 0.5 * erfc(-0.7071067811865475 * A) + 0.5 * erfcx(0.7071067811865475 * B) * exp(-0.5 * A * A);
+        // with a' = A / sqrt 2, b' = B / sqrt 2 >= |a'| and E = e^{-a'^2}:
+        //   a' <  0:  F = E/2 (erfcx(-a') + erfcx(b'))        (erfc(-a') = E erfcx(-a'))
+        //   a' >= 0:  F = 1 - E/2 (erfcx(a') - erfcx(b'))     (erfc(-a') = 2 - E erfcx(a'))
+        // two single-path erfcx and ONE exponential
+        const double ap = 0.7071067811865475 * A, bp = 0.7071067811865475 * B;
+        const double e1 = fm::erfcx_pos(fabs(ap)), e2 = fm::erfcx_pos(bp);
+        const double hE = 0.5 * fm::exp_neg_sq(ap);
+        F = ap < 0.0 ? hE * (e1 + e2) : 1.0 - hE * (e1 - e2);
         return true;
     }
     const double t = 0.5 * a / sx;  // sx = sqrt(2x)
     if (t > 26.55) return false;
-    F = erfc(t);
+    F = fm::erfcx_pos(t) * fm::exp_neg_sq(t);
     return true;
 }
 

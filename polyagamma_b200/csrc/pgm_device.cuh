@@ -269,6 +269,42 @@ sincos2pi(double u, double& s_out, double& c_out)
     s_out = (q & 2) ? -s0 : s0;
 }
 
+// erfcx(z) = e^{z^2} erfc(z) for finite z >= 0 on ONE code path: (1 + z/4) erfcx(z) is smooth in
+// t = 1 / (1 + z/4) on (0, 1] and a 24-term Chebyshev series in 2t - 1 (Clenshaw recurrence) gives
+// <= 2e-15 relative (tools/gen_erfcx_table.py: coefficients from mpmath, error check of this very
+// recurrence; tests/test_gpu_parity.py::test_fast_math).  Used by the cdf / logcdf kernels; in the
+// sampler setups libdevice's erfc measured marginally faster (one call per element, no loop) and stays.
+// libdevice's erf/erfc/erfcx switch between range-specific kernels, which the lanes of a warp with
+// mixed arguments run one after the other.
+static __constant__ double c_erfcx[24] = {
+#include "pgm_erfcx_table.inc"
+};
+
+__device__ __forceinline__ double
+erfcx_pos(double z)
+{
+    const double t = rcp(fma(0.25, z, 1.0));
+    const double u2 = fma(4.0, t, -2.0);  // 2 (2t - 1)
+    double b1 = 0.0, b2 = 0.0;
+#pragma unroll
+    for (int k = 23; k >= 1; --k) {
+        const double b0 = fma(u2, b1, c_erfcx[k] - b2);
+        b2 = b1;
+        b1 = b0;
+    }
+    return t * fma(0.5 * u2, b1, c_erfcx[0] - b2);
+}
+
+// e^{-x^2} with the rounding error of the square carried along (x^2 up to ~700 would otherwise cost
+// 7e-14 of relative accuracy)
+__device__ __forceinline__ double
+exp_neg_sq(double x)
+{
+    const double hi = x * x;
+    const double lo = fma(x, x, -hi);
+    return exp(-hi) * (1.0 - lo);
+}
+
 }  // namespace fm
 
 // One private stream per output element: words of Philox(call key, ctr = (idx, block, 0)),

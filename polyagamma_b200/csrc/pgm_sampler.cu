@@ -1042,6 +1042,8 @@ test_math_kernel(int which, const double* __restrict__ in, size_t n, double* __r
             case 6: fm::sincos2pi(x, y, t); break;
             case 7: fm::sincos2pi(x, t, y); break;
             case 9: y = pgm_lgamma(x); break;
+            case 10: y = fm::erfcx_pos(x); break;
+            case 11: y = fm::erfcx_pos(x) * fm::exp_neg_sq(x); break;  // erfc(x), x >= 0, as the cdf kernels form it
             default: y = fm::div(1.0, x); break;
         }
         out[i] = y;

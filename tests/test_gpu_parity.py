@@ -336,6 +336,18 @@ def test_fast_math(torch):
                          np.arange(1.0, 201.0), np.array([0.5, 1.5, 6.999999, 7.0, 7.000001, 201.0, 1e-300])])
     got, want = run(9, xs), gammaln(xs)
     assert float(np.max(np.abs(got - want) / np.maximum(1.0, np.abs(want)))) <= 2e-14
+    # single-path erfcx / erfc (24-term Chebyshev series, tools/gen_erfcx_table.py)
+    from scipy.special import erfcx
+
+    zs = np.concatenate([rng.uniform(0, 40, n), 10.0 ** rng.uniform(-12, 12, n // 4), np.array([0.0, 1e-300, 1e299])])
+    assert ulps(run(10, zs), erfcx(zs)) <= 16.0  # 9 observed: 2e-15 relative
+    # erfc(x) = erfcx(x) e^{-x^2} with the compensated square, against mpmath (scipy's erfc squares its
+    # argument uncompensated and is itself off by x^2 eps ~ 6e-14 at x = 26)
+    import mpmath
+
+    xe = np.concatenate([rng.uniform(0, 26.5, 400), np.abs(rng.normal(0, 1, 100)), np.array([0.0, 26.54])])
+    want = np.array([float(mpmath.erfc(mpmath.mpf(float(v)))) for v in xe])
+    assert float(np.max(np.abs(run(11, xe) - want) / want)) <= 5e-15
     # special arguments fall back to libdevice semantics
     sp = np.array([0.0, np.inf, np.nan, -1.0, 5e-324])
     with np.errstate(all="ignore"):
