@@ -135,18 +135,20 @@ uint64_t pgm_cuda_launch_count(void);
 /* Per-kernel device time, for roofline accounting.  Between _begin and _end every kernel this
  * library launches is bracketed by CUDA events on its own stream; _end synchronises those
  * events and returns, per kernel kind, the summed milliseconds and the launch count.
- * Kinds: 0 classify, 1 scan, 2 scatter; sampling kernels 3 devroye, 4 alternate, 5 saddle (both
- * envelope pieces), 6 saddle-left (left piece only, |z| < 8), 7 saddle-far (left piece, |z| >= 14),
- * 8 alternate-left (left piece only, |z| >= 14), 9 saddle-mid (the far kernel on 8 <= |z| < 14);
- * 10 normal, 11 gamma, 12 density; per-element setup kernels 13..19 in the order of 3..9;
- * 20 psi = X beta, 21 weighted Gram matrix.  `cap` = length of both output arrays (>= 22). */
+ * Kinds: 0 the one-pass bucketing kernel (1 and 2 are unused: they were its scan and scatter passes);
+ * sampling kernels 3 devroye (both proposal variants), 4 alternate, 5 saddle (both envelope pieces),
+ * 6 saddle-left (left piece only, |z| < 8), 7 saddle-far (left piece, |z| >= 14), 8 alternate-left (left
+ * piece only, |z| >= 14), 9 saddle-mid (the far kernel on 8 <= |z| < 14); 10 normal, 11 gamma,
+ * 12 density; per-element setup kernels 13..19 in the order of 3..9 (7, 8 and 9 compute their records
+ * inside the sampling kernel: no setup launch); 20 psi = X beta, 21 weighted Gram matrix.
+ * `cap` = length of both output arrays (>= 22). */
 #define PGM_CUDA_NUM_KERNEL_KINDS 22
 void pgm_cuda_profile_begin(void);
 int pgm_cuda_profile_end(double* ms, uint64_t* launches, int cap);
 /* FP64 (DFMA) peak of the current device in TFLOP/s, measured by a register-resident FMA
  * microbenchmark: the denominator of the FP64 roofline.  Synchronises `stream`. */
 int pgm_cuda_fp64_peak_tflops(double* tflops, void* stream);
-/* The per-pass scratch (up to ~80 B per element of a 2^27-element pass) is allocated stream-ordered
+/* The per-pass scratch (up to ~108 B per element of a 2^27-element pass: nine index lists and the records) is allocated stream-ordered
  * from the device's default memory pool and stays cached there between calls.  This returns the
  * cached blocks of the current device to the driver (synchronises the device). */
 int pgm_cuda_release_scratch(void);

@@ -9,7 +9,7 @@
 //                               dense_kernel, over that bucket's list
 //   explicit: the same kernels over the identity list
 //
-// persistent_kernel: every lane owns one element at a time and advances it by ONE proposal
+// sample_kernel: every lane owns one element at a time and advances it by ONE proposal
 // attempt per loop trip (pgm_methods.cuh); lanes whose element completed are retired and
 // refilled from a per-bucket work counter, found with __ballot_sync/__popc, so a warp never
 // idles on another lane's rejection loop.  Nothing here synchronises the host.
@@ -403,7 +403,7 @@ setup_kernel(FillArgs a, Bucket b)
         load_hz(a, g, h, z);
         double rec[M::kFields];
         if (invalid_h(h, bad)) {
-            // only reachable on the identity range (classify_kernel filters invalid h itself)
+            // only reachable on the identity range (bucket_kernel filters invalid h itself)
             if (!b.uniform) a.out[g] = bad;
 #pragma unroll
             for (int f = 0; f < M::kFields; ++f) rec[f] = NAN;
