@@ -742,7 +742,7 @@ env_chunk_log2()
     const char* e = getenv("PGM_CUDA_CHUNK_LOG2");
     if (e == nullptr) return 0;
     int v = atoi(e);
-    return (v >= 10 && v <= 30) ? v : 0;
+    return (v >= 10 && v <= 28) ? v : 0;  // 9 lists x 2^28 entries still index with 32 bits
 }
 
 static int
