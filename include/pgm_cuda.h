@@ -135,7 +135,7 @@ uint64_t pgm_cuda_launch_count(void);
 /* Per-kernel device time, for roofline accounting.  Between _begin and _end every kernel this
  * library launches is bracketed by CUDA events on its own stream; _end synchronises those
  * events and returns, per kernel kind, the summed milliseconds and the launch count.
- * Kinds: 0 the one-pass bucketing kernel (1 and 2 are unused: they were its scan and scatter passes);
+ * Kinds: 0 the one-pass bucketing kernel, 1 the one-launch kernel of small fills (2 is unused);
  * sampling kernels 3 devroye (both proposal variants), 4 alternate, 5 saddle (both envelope pieces),
  * 6 saddle-left (left piece only, |z| < 8), 7 saddle-far (left piece, |z| >= 14), 8 alternate-left (left
  * piece only, |z| >= 14), 9 saddle-mid (the far kernel on 8 <= |z| < 14); 10 normal, 11 gamma,

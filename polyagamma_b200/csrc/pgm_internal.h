@@ -58,9 +58,9 @@ int launch_test_math(int which, const double* d_in, size_t n, double* d_out, cud
 
 // kernel kinds reported by pgm_cuda_profile_end
 enum : int {
-    kKindClassify = 0,
-    kKindScan = 1,
-    kKindScatter = 2,
+    kKindClassify = 0,  // the one-pass bucketing kernel
+    kKindSmall = 1,     // the one-launch kernel for small fills
+    kKindUnused2 = 2,
     // sampling kernels: + 0 devroye, 1 alternate, 2 saddle, 3 saddle-left, 4 saddle-far, 5 alternate-left,
     // 6 saddle-mid
     kKindDevroye = 3,

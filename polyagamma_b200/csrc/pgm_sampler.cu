@@ -587,6 +587,66 @@ dense_kernel(FillArgs a, Bucket b)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// small fills: ONE launch, one thread per element
+// ---------------------------------------------------------------------------------------
+// The bucketed pipeline costs one bucketing launch, up to fifteen method launches (sized for the whole
+// pass, since the bucket sizes stay on the device), a scratch allocation and stream joins: 100-300 us
+// per call whatever the size.  A Gibbs sampler calls with 1e3..1e5 elements per sweep, where that
+// overhead is the whole cost.  Below kSmallMax elements every thread takes one element through the
+// SAME per-bucket code the pipeline would run (same record, same step function, same Philox stream: the
+// result is bit-identical), to completion: divergent, but one launch and no scratch.
+template <class M>
+__device__ __noinline__ double
+run_one(uint32_t k0, uint32_t k1, uint64_t index, double h, double z, bool compat)
+{
+    double rec[M::kFields];
+    M::make_record(h, z, compat, rec);
+    typename M::Par par;
+    typename M::State st;
+    if (!M::load(LocalRec{rec}, par, st, compat)) return 0.0;  // devroye with floor(h) == 0
+    PhiloxKey key;  // (the samplers' generators use k0, k1 only; the round keys serve the dense normal kernel)
+    key.k0 = k0;
+    key.k1 = k1;
+    typename M::Rng rng;
+    rng.init(key, index);
+    while (!M::step(par, st, rng, compat)) {
+    }
+    return st.acc;
+}
+
+__global__ void __launch_bounds__(128)
+small_kernel(FillArgs a, uint32_t n, int method)
+{
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const bool compat = a.compat != 0;
+    const uint64_t g = a.base + e;
+    double h, z, v;
+    load_hz(a, g, h, z);
+    if (!invalid_h(h, v)) {
+        const int m = (method == kHybrid) ? hybrid_select(h, z) : method;
+        const uint32_t k0 = a.key.k0, k1 = a.key.k1;
+        const uint64_t index = a.first_index + g;
+        switch (bucket_of(m, h, z, compat)) {
+            case kBDevroye: v = run_one<DevroyeT<kDevroyePair>>(k0, k1, index, h, z, compat); break;
+            case kBDevroyeMSH: v = run_one<DevroyeT<kDevroyeMSH>>(k0, k1, index, h, z, compat); break;
+            case kBAlternate: v = run_one<Alternate>(k0, k1, index, h, z, compat); break;
+            case kBAlternateLeft: v = run_one<AlternateLeft>(k0, k1, index, h, z, compat); break;
+            case kBSaddleFull: v = run_one<SaddleFull>(k0, k1, index, h, z, compat); break;
+            case kBSaddleLeft: v = run_one<SaddleLeft>(k0, k1, index, h, z, compat); break;
+            case kBSaddleFar:
+            case kBSaddleMid: v = run_one<SaddleFar>(k0, k1, index, h, z, compat); break;
+            default: {  // kBNormal
+                RngInlineRK r;
+                r.init(a.key, a.first_index + g);
+                v = normal_approx_sample(r, h, z);
+            }
+        }
+    }
+    a.out[g] = v;
+}
+
 // fills g_guess_uc / g_guess_ur (one thread per table entry)
 __global__ void
 init_guess_tables_kernel()
@@ -735,6 +795,7 @@ launch_dense(const DeviceInfo& d, const FillArgs& a, const Bucket& b, uint64_t c
 // allocation of the scratch fails.  PGM_CUDA_CHUNK_LOG2 in the environment pins the pass size
 // (tests use it to cross pass seams).
 constexpr int kChunkLog2Min = 20, kChunkLog2Max = 27;
+constexpr uint64_t kSmallMaxDefault = 1ull << 16;  // mixed-method fills break even near 1e5, single-method ones far later
 
 static int
 env_chunk_log2()
@@ -760,6 +821,14 @@ align256(size_t v)
     return (v + 255) & ~size_t(255);
 }
 
+// largest fill that takes the one-launch path (PGM_CUDA_SMALL_MAX overrides; 0 disables it)
+static uint64_t
+small_max()
+{
+    const char* e = getenv("PGM_CUDA_SMALL_MAX");  // read per call: the tests switch it
+    return e ? (uint64_t)strtoull(e, nullptr, 10) : kSmallMaxDefault;
+}
+
 int
 launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
 {
@@ -770,6 +839,13 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     const bool compat = a.compat != 0;
     DeviceInfo d = device_info();
     cudaError_t err;
+
+    if (m != kGamma && n <= small_max()) {
+        ScopedKernelTimer timer(kKindSmall, s);
+        small_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(a, (uint32_t)n, m);
+        count_launch(1);
+        return (int)cudaGetLastError();
+    }
 
     const bool scalar_params = (a.h == nullptr && a.z == nullptr && a.bc.ndim == 0);
     if (scalar_params) {

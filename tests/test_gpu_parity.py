@@ -294,6 +294,36 @@ def test_c_abi_direct_call(torch, oracle):
     assert v == oracle.fill(11, 4, 1.0, 0.0, 1)[0] or abs(v / oracle.fill(11, 4, 1.0, 0.0, 1)[0] - 1) < 1e-9
 
 
+@pytest.mark.parametrize("method", [None, "devroye", "alternate", "saddle"])
+@pytest.mark.parametrize("compat", [False, True])
+def test_small_fill_path_equals_pipeline(pg, torch, monkeypatch, method, compat):
+    """Fills of up to 2^16 elements take ONE launch (a thread per element through the same per-bucket
+    code); the result must be bit-identical to the bucketed pipeline's, arrays and scalars."""
+    rng = np.random.default_rng(17)
+    n = 60_001
+    if method == "devroye":
+        h = rng.integers(1, 5, n).astype(float)
+    elif method == "alternate":
+        h = rng.uniform(0.2, 9.0, n)
+    elif method == "saddle":
+        h = rng.uniform(1.0, 120.0, n)
+    else:
+        h = rng.uniform(0.1, 200.0, n)
+        h[::7] = rng.integers(1, 5, h[::7].size)  # integer shapes: devroye / alternate by z
+    z = rng.uniform(-50, 50, n)
+    z[::5] = rng.normal(0, 1.5, z[::5].size)
+    h[:4] = [np.nan, -2.0, np.inf, 0.0]
+    kw = dict(method=method, random_state=(99, 7), disable_checks=True, ref_compat=compat)
+    monkeypatch.setenv("PGM_CUDA_SMALL_MAX", "0")
+    want = pg.random_polyagamma(h, z, **kw)
+    want_s = pg.random_polyagamma(2.5 if method != "devroye" else 3.0, 1.25, size=20_000, **kw)
+    monkeypatch.delenv("PGM_CUDA_SMALL_MAX")
+    got = pg.random_polyagamma(h, z, **kw)
+    got_s = pg.random_polyagamma(2.5 if method != "devroye" else 3.0, 1.25, size=20_000, **kw)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.array_equal(got_s, want_s)
+
+
 def test_fast_math(torch):
     """The kernels' own elementary functions (fm:: in csrc/pgm_device.cuh) against numpy's libm over
     the argument ranges the samplers produce."""
