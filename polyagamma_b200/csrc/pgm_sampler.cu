@@ -840,7 +840,14 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     DeviceInfo d = device_info();
     cudaError_t err;
 
-    if (m != kGamma && n <= small_max()) {
+    // with ONE shape for the whole call the elements fall into two or three buckets at most, a warp of
+    // the one-launch kernel serialises correspondingly few code paths, and it wins up to 4x further
+    bool one_shape = (a.h == nullptr || a.h_stride == 0);
+    if (a.bc.ndim != 0) {
+        one_shape = true;
+        for (int dd = 0; dd < a.bc.ndim; ++dd) one_shape = one_shape && a.bc.hs[dd] == 0;
+    }
+    if (m != kGamma && n <= small_max() * (one_shape ? 4 : 1)) {
         ScopedKernelTimer timer(kKindSmall, s);
         small_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, s>>>(a, (uint32_t)n, m);
         count_launch(1);
