@@ -55,13 +55,13 @@ FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 508.0, "alternate_left": 384
 DRAM_BYTES_PER_ELEMENT = {"normal": 42.0, "saddle_far": 146.9, "saddle_mid": 270.6, "saddle_left": 104.3,
                           "saddle": 115.8, "alternate": 75.3, "alternate_left": 275.6,
                           "setup_saddle_left": 241.2, "setup_saddle": 256.4, "setup_alternate": 253.8}
-KERNEL_NAMES = {"devroye": "sample_kernel<Devroye>", "alternate": "sample_kernel<Alternate>",
+KERNEL_NAMES = {"devroye": "sample_kernel<DevroyeT<pair|MSH>>", "alternate": "sample_kernel<Alternate>",
                 "alternate_left": "sample_kernel<AlternateLeft, fused setup>", "setup_alternate_left": "setup_kernel<AlternateLeft>",
                 "saddle": "sample_kernel<SaddleFull>", "saddle_left": "sample_kernel<SaddleLeft>",
                 "saddle_far": "sample_kernel<SaddleFar, fused setup>", "saddle_mid": "sample_kernel<SaddleFar, fused setup> (8<=|z|<14)",
                 "setup_saddle_mid": "setup_kernel<SaddleFar> (8<=|z|<14)",
                 "normal": "dense_kernel<normal>", "gamma": "dense_kernel<gamma>",
-                "setup_devroye": "setup_kernel<Devroye>", "setup_alternate": "setup_kernel<Alternate>",
+                "setup_devroye": "setup_kernel<DevroyeT<pair|MSH>>", "setup_alternate": "setup_kernel<Alternate>",
                 "setup_saddle": "setup_kernel<SaddleFull>", "setup_saddle_left": "setup_kernel<SaddleLeft>",
                 "setup_saddle_far": "setup_kernel<SaddleFar>"}
 BYTES_PER_ELEMENT = 24 + 4  # h, z in + out + the 4-byte list index of the bucketing pass

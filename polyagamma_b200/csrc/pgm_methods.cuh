@@ -49,8 +49,8 @@ using RngFor = RngT<((PGM_RNG_OUTLINE_MASK >> BIT) & 1) != 0>;
 // LEFT fixes the proposal of the truncated inverse-Gaussian piece at compile time: the hybrid
 // dispatch buckets devroye elements by |z|/2 < 1/T (exponential pairs) or not (Michael-Schucany-Haas)
 // so that the lanes of a warp do not serialise the two (cfg2, z ~ N(0, 3): 70 % / 30 %; 13.5 of 32
-// lanes active when mixed).  kDevroyeAny decides per element (explicit method on the identity range).
-enum : int { kDevroyeAny = 0, kDevroyePair = 1, kDevroyeMSH = 2 };
+// lanes active when mixed); the explicit devroye method goes through the same bucketing.
+enum : int { kDevroyePair = 1, kDevroyeMSH = 2 };
 
 template <int LEFT>
 struct DevroyeT {
@@ -136,7 +136,7 @@ struct DevroyeT {
         const double L = -log(r.uniform_oc());
         if (left) {
             s.in_left = 1;
-            const bool pair = LEFT == kDevroyePair ? true : LEFT == kDevroyeMSH ? false : (p.zz < 1.5625);
+            constexpr bool pair = LEFT == kDevroyePair;
             if (pair) {  // |z|/2 < 1/T: exponential-pair proposal of Devroye (2009)
                 const double e2 = r.exponential();
                 if (L * L > 3.125 * e2) return false;
@@ -194,8 +194,6 @@ struct DevroyeT {
         return false;
     }
 };
-
-using Devroye = DevroyeT<kDevroyeAny>;
 
 // =========================================================================================
 // Alternate: J*(h, z) for h <= 4, chunked above             (src/pgm_alternate.c)
