@@ -78,16 +78,30 @@ struct DevroyeT {
         if (!(zz > 0.0)) zz = 0.0;  // z = NaN is sampled as z = 0
         double w, K;
         if (zz > 0.0) {
+            // p = erfc(a - b) e^{-zz} + erfc(a + b) e^{zz} and q = (pi/2) e^{-K T} / K with a = 1 / sqrt(2T),
+            // b = zz sqrt(T/2), 2ab = zz: every term carries E = e^{-(a^2 + b^2)} --
+            //   erfc(a -+ b) e^{-+zz} = erfcx(a -+ b) E,      e^{-K T} = E e^{a^2 - pi^2 T / 8}
+            // -- so p / (p + q) needs no exponential at all while a >= b, and one (of (b - a)^2, through
+            // erfc(a - b) = 2 - erfc(b - a)) otherwise: two single-path erfcx instead of two erfc and
+            // three exp.
             const double a = 0.8838834764831844;  // 1 / sqrt(2T)
             const double tt = 0.565685424949238;  // sqrt(T / 2)
-            double b = zz * tt;
-            double t1 = erfc(a - b) * exp(-zz);
-            double t2 = (a + b < 26.5) ? erfc(a + b) * exp(zz) : 0.0;
-            double pp = t1 + t2;
+            const double b = zz * tt;
+            const double d = b - a;
             K = kPi2_8 + 0.5 * zz * zz;
-            double q = kPi_2 * exp(-K * T) * fm::rcp(K);
-            // (the sum underflows only for |z| far beyond any finite-variance use: IEEE division there)
-            w = (pp + q > 1e-290) ? fm::div(pp, pp + q) : (pp + q > 0.0) ? pp / (pp + q) : 1.0;
+            const double Q = 1.557784085126967 * fm::rcp(K);  // (pi/2) e^{a^2 - pi^2 T / 8} / K
+            const double e1 = fm::erfcx_pos(fabs(d)), e2 = fm::erfcx_pos(a + b);
+            if (d <= 0.0) {
+                const double P = e1 + e2;
+                w = fm::div(P, P + Q);
+            }
+            else if (d * d < 600.0) {
+                const double P = 2.0 * exp(d * d) - e1 + e2;
+                w = fm::div(P, P + Q);
+            }
+            else {
+                w = 1.0;  // q / p < 1e-260
+            }
         }
         else {
             w = 0.4223027567786595;  // src/pgm_devroye.c:78
