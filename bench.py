@@ -41,10 +41,10 @@ WORKLOAD = "cfg4: fill2 hybrid, h~U[0.1,200], z~U[-50,50] (BASELINE.json configs
 # instructions 2*DFMA + DMUL + DADD (ncu smsp__sass_thread_inst_executed_op_d{fma,mul,add}_pred_on)
 # of one profiled launch divided by the elements of that launch -- profiles/r1j_cfg4_all_kernels.txt,
 # table in profiles/README.md (SURVEY 8(d)'s nominal per-method figures are kept beside them there).
-# devroye figures are from the cfg2 capture (cfg4 has no devroye elements).
+# devroye figures are from the cfg2 capture (cfg4 has no devroye elements; its setup is fused as well).
 FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 508.0, "alternate_left": 384.0, "saddle": 600.0,
                      "saddle_left": 640.0, "saddle_far": 577.0, "saddle_mid": 645.0, "normal": 152.0, "gamma": 6.0e4,
-                     "setup_devroye": 356.0, "setup_alternate": 1091.0, "setup_saddle": 1654.0,
+                     "setup_devroye": 0.0, "setup_alternate": 1091.0, "setup_saddle": 1654.0,
                      "setup_saddle_left": 354.0,
                      # the far / mid saddle and alternate-left buckets compute their records inside the
                      # sampling kernel: no setup launch, the sampling figure includes the setup

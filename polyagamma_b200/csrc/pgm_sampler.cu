@@ -753,10 +753,11 @@ grid_for(uint64_t full, uint64_t count_hint, uint32_t threads)
 // kKindDevroye / kKindSetup + which)
 // Which buckets compute their records inside the sampling kernel (measured on cfg4, ms per 1e9,
 // setup + sampling separate -> fused): saddle-far 8.25 -> 6.86, saddle-mid 2.71 -> 2.44, alternate-left
-// 2.04 -> 1.55; saddle-left gets slower (3.83 -> 4.22: its setup is longer and its lanes refill out
-// of step), and the full saddle / alternate setups are the big ones the split exists for.
+// 2.04 -> 1.55, devroye (cfg3, per 1e8) 5.23 -> 5.04; saddle-left gets slower (3.83 -> 4.22: its setup is
+// longer and its lanes refill out of step), and the full saddle / alternate setups are the big ones the
+// split exists for.
 constexpr bool kFuseFar = true, kFuseMid = true, kFuseLeft = false, kFuseAltLeft = true;
-constexpr bool kFuseDevroye = false;  // cfg2: 13.9 -> 12.5e9 samples/s when fused (two erfc in the refill)
+constexpr bool kFuseDevroye = true;  // cfg3 devroye 19.1 -> 19.8e9 with the exponential-free setup (slower with the erfc one)
 
 template <class M, bool FUSED = false>
 static void
