@@ -259,15 +259,19 @@ struct Alternate {
         double a = h * fm::rsqrt(2.0 * t);
         if (zz > 0.0) {
             lambda = kPi2_8 + 0.5 * zz * zz;
-            double b = zz * sqrt(0.5 * t);
-            double hz = h * zz;
-            double t1 = 0.5 * erfc(a - b) * exp(-hz);
-            double t2 = (a + b < 26.5 && hz < 700.0) ? 0.5 * erfc(a + b) * exp(hz) : 0.0;
-            lp = hlog2 + log(t1 + t2);
+            // invgauss_cdf (src/pgm_alternate.c:104-114): 1/2 [erfc(a - b) e^{-hz} + erfc(a + b) e^{hz}] with
+            // 2ab = hz, so both terms carry e^{-(a^2 + b^2)} (see Devroye::make_record):
+            //   a >= b:  log = -(a^2 + b^2) + log(1/2 (erfcx(a - b) + erfcx(a + b)))
+            //   a <  b:  log = -hz + log1p(1/2 e^{-(b-a)^2} (erfcx(a + b) - erfcx(b - a)))
+            const double b = zz * sqrt(0.5 * t);
+            const double d = b - a;
+            const double e1 = fm::erfcx_pos(fabs(d)), e2 = fm::erfcx_pos(a + b);
+            if (d <= 0.0) lp = hlog2 - (a * a + b * b) + log(0.5 * (e1 + e2));
+            else lp = hlog2 - h * zz + log1p(0.5 * fm::exp_neg_sq(d) * (e2 - e1));
         }
         else {
             lambda = kPi2_8;
-            lp = hlog2 + log(erfc(a));
+            lp = hlog2 - a * a + log(fm::erfcx_pos(a));  // log erfc(a)
         }
         double lq = h * (kLogPi_2 - log(lambda)) + log_upper_gamma(h, lambda * t, true, lgammah);
         w_right = 1.0 / (1.0 + exp(lp - lq));
@@ -691,11 +695,16 @@ __device__ __forceinline__ double
 invgauss_logcdf(double x, double mu, double lambda)
 {
     // (x, mu, lambda are positive normal numbers here: MUFU-seeded reciprocals)
-    double qm = fm::div(x, mu);
-    double rr_inv = fm::rsqrt(fm::div(x, lambda));
-    double a = log_ndtr((qm - 1.0) * rr_inv);
-    double b = 2.0 * fm::div(lambda, mu) + log_ndtr(-(qm + 1.0) * rr_inv);
-    return a + log1p(exp(b - a));
+    // cdf = Phi(A) + e^{2 lambda / mu} Phi(-B); with a' = A / sqrt 2, b' = B / sqrt 2 the exponent is
+    // b'^2 - a'^2, so both terms carry e^{-a'^2} (the devroye setup's identity):
+    //   a' <  0:  log cdf = -a'^2 + log(1/2 (erfcx(-a') + erfcx(b')))
+    //   a' >= 0:  log cdf = log1p(-1/2 e^{-a'^2} (erfcx(a') - erfcx(b')))
+    const double qm = fm::div(x, mu);
+    const double s = 0.7071067811865475 * fm::rsqrt(fm::div(x, lambda));
+    const double ap = (qm - 1.0) * s, bp = (qm + 1.0) * s;
+    const double e1 = fm::erfcx_pos(fabs(ap)), e2 = fm::erfcx_pos(bp);
+    if (ap < 0.0) return log(0.5 * (e1 + e2)) - ap * ap;
+    return log1p(-0.5 * fm::exp_neg_sq(ap) * (e1 - e2));
 }
 
 }  // namespace saddle
