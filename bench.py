@@ -44,7 +44,7 @@ WORKLOAD = "cfg4: fill2 hybrid, h~U[0.1,200], z~U[-50,50] (BASELINE.json configs
 # devroye figures are from the cfg2 capture (cfg4 has no devroye elements; its setup is fused as well).
 FLOPS_PER_ELEMENT = {"devroye": 254.0, "alternate": 508.0, "alternate_left": 384.0, "saddle": 600.0,
                      "saddle_left": 640.0, "saddle_far": 577.0, "saddle_mid": 645.0, "normal": 152.0, "gamma": 6.0e4,
-                     "setup_devroye": 0.0, "setup_alternate": 1091.0, "setup_saddle": 1654.0,
+                     "setup_devroye": 0.0, "setup_alternate": 1006.0, "setup_saddle": 1569.0,
                      "setup_saddle_left": 354.0,
                      # the far / mid saddle and alternate-left buckets compute their records inside the
                      # sampling kernel: no setup launch, the sampling figure includes the setup
