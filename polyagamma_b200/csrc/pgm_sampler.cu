@@ -1026,8 +1026,27 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     }
     cudaStream_t sb = overlap ? hb : s;
     cudaStream_t s1 = multi ? h1 : s, s2 = multi ? h2 : s;
-    cudaEvent_t ev[8];  // 0 ready, 1-2 prep[buf], 3-4 used[buf], 5 go, 6-7 helper streams done
-    for (auto& e : ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    // 0 ready, 1-2 prep[buf], 3-4 used[buf], 5 go, 6-7 helper streams done.  One set per host thread
+    // and device, created once: a wait captures the record that precedes it, so re-recording an event
+    // in the next call cannot disturb the waits of this one, and no other thread touches the set.
+    struct EventSet {
+        cudaEvent_t ev[8];
+        bool ready = false;
+    };
+    static thread_local EventSet t_events[64];
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    EventSet& es = t_events[cur_dev & 63];
+    if (!es.ready) {
+        for (auto& e : es.ev) {
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+                cudaFreeAsync(ws, s);
+                return (int)cudaGetLastError();
+            }
+        }
+        es.ready = true;
+    }
+    cudaEvent_t* ev = es.ev;
     cudaEvent_t ev_ready = ev[0], *ev_prep = ev + 1, *ev_used = ev + 3, ev_go = ev[5], *ev_done = ev + 6;
     cudaEventRecord(ev_ready, s);  // inputs and the scratch allocation are ordered before this point
     if (overlap) cudaStreamWaitEvent(sb, ev_ready, 0);
@@ -1061,7 +1080,6 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         if (overlap) cudaEventRecord(ev_used[buf], s);
     }
     cudaFreeAsync(ws, s);
-    for (auto& e : ev) cudaEventDestroy(e);  // destruction is deferred until the events have completed
     return (int)cudaGetLastError();
 }
 
