@@ -695,8 +695,10 @@ static DeviceInfo
 device_info()
 {
     static DeviceInfo cache[64];
+    static std::mutex mu;  // first calls from several host threads: one of them fills the entry, the others wait
     int dev = 0;
     cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
     DeviceInfo& d = cache[dev & 63];
     if (d.sms == 0) {
         cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
