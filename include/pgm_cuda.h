@@ -19,6 +19,12 @@
  *
  * No torch types, no C++ types.  The library allocates only stream-ordered scratch
  * (`cudaMallocAsync`) for the method-bucketing pass; every in/out buffer is caller-owned.
+ *
+ * Threads: every entry point may be called from several host threads at once, each on its own
+ * stream (the reference serialises callers with the BitGenerator's lock,
+ * polyagamma/_polyagamma.pyx:172-176; here a call owns no generator state -- its draws are named by
+ * (seed, offset, index)).  Concurrent calls produce exactly what the same calls produce one after
+ * the other (tests/test_gpu_threads.py).
  */
 #ifndef PGM_CUDA_H
 #define PGM_CUDA_H
