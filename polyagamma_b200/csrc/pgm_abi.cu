@@ -141,13 +141,7 @@ pgm_cuda_logistic_omega_step(uint64_t seed, uint64_t offset, const double* d_X, 
 int
 pgm_cuda_release_scratch(void)
 {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return (int)e;
-    cudaMemPool_t pool;
-    if ((e = cudaDeviceGetDefaultMemPool(&pool, dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;
-    return (int)cudaMemPoolTrimTo(pool, 0);
+    return pgm::scratch_release();
 }
 
 int
@@ -360,7 +354,7 @@ pgm_cuda_any_invalid_h(const double* d_h, size_t n, int method, int* result, voi
     cudaStream_t s = (cudaStream_t)stream;
     int* d_flag = nullptr;
     cudaError_t e;
-    if ((e = cudaMallocAsync(&d_flag, sizeof(int), s)) != cudaSuccess) return (int)e;
+    if ((e = (cudaError_t)pgm::scratch_alloc((void**)&d_flag, sizeof(int), s)) != cudaSuccess) return (int)e;
     cudaMemsetAsync(d_flag, 0, sizeof(int), s);
     int rc = launch_check_h(d_h, n, (method & 0xff) == kDevroye, d_flag, s);
     if (rc == 0) {
@@ -479,7 +473,7 @@ pgm_cuda_polyagamma_density_host(int which, const double* x, int x_stride, const
     int rc = 0;
     for (int k = 0; k < 4 && rc == 0; ++k) {
         const size_t len = (k < 3 && strides[k] == 0) ? 1 : chunk;
-        rc = (int)cudaMallocAsync(&d[k], len * sizeof(double), s);
+        rc = pgm::scratch_alloc((void**)&d[k], len * sizeof(double), s);
     }
     for (int k = 0; k < 3 && rc == 0; ++k)
         if (strides[k] == 0) rc = (int)cudaMemcpyAsync(d[k], src[k], sizeof(double), cudaMemcpyHostToDevice, s);

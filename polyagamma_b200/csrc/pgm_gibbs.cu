@@ -298,7 +298,7 @@ launch_logistic_omega_step(uint64_t seed, uint64_t offset, const double* d_X, si
     const size_t omega_bytes = d_omega ? 0 : ((n * sizeof(double) + 255) & ~size_t(255));
     const size_t psi_bytes = d_psi ? 0 : ((n * sizeof(double) + 255) & ~size_t(255));
     const size_t part_bytes = (size_t)gram_blocks * gs.ntiles * 64 * sizeof(double);
-    if ((err = cudaMallocAsync(&ws, omega_bytes + psi_bytes + part_bytes, s)) != cudaSuccess) return (int)err;
+    if ((err = (cudaError_t)scratch_alloc((void**)&ws, omega_bytes + psi_bytes + part_bytes, s)) != cudaSuccess) return (int)err;
     double* omega = d_omega ? d_omega : (double*)ws;
     double* psi = d_psi ? d_psi : (double*)(ws + omega_bytes);
     double* partial = (double*)(ws + omega_bytes + psi_bytes);

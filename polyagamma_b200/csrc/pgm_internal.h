@@ -51,6 +51,9 @@ int launch_density(int which, DensityArgs a, uint64_t n, cudaStream_t s);
 int launch_logistic_omega_step(uint64_t seed, uint64_t offset, const double* d_X, size_t n, int p, size_t ldx,
                                const double* d_beta, const double* d_ntrials, double ntrials_scalar, int method,
                                double* d_gram, double* d_omega, double* d_psi, uint64_t first_index, cudaStream_t s);
+int device_init();                                          // per-device one-time setup (tables, scratch pool)
+int scratch_alloc(void** p, size_t bytes, cudaStream_t s);  // stream-ordered, from the library's private pool
+int scratch_release();
 uint64_t launch_count();
 void count_launch(uint64_t n);
 int measure_fp64_peak(double* tflops, cudaStream_t s);
@@ -58,9 +61,9 @@ int launch_test_math(int which, const double* d_in, size_t n, double* d_out, cud
 
 // kernel kinds reported by pgm_cuda_profile_end
 enum : int {
-    kKindClassify = 0,  // the one-pass bucketing kernel
+    kKindClassify = 0,  // (round 1: the one-pass bucketing kernel; unused)
     kKindSmall = 1,     // the one-launch kernel for small fills
-    kKindUnused2 = 2,
+    kKindTile = 2,      // tile kernel: classify + in-tile normal / far saddle / devroye + list compaction
     // sampling kernels: + 0 devroye, 1 alternate, 2 saddle, 3 saddle-left, 4 saddle-far, 5 alternate-left,
     // 6 saddle-mid
     kKindDevroye = 3,

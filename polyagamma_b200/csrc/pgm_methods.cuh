@@ -592,9 +592,20 @@ kprime3(double u, double& f, double& fp, double& fpp)
         tt = tan(s);
     }
     else {
-        // tanh s = (1 - e^{-2s}) / (1 + e^{-2s}); below s = 0.1 the subtraction would cost digits
+        // tanh s = (1 - e^{-2s}) / (1 + e^{-2s}); below s = 0.1 the subtraction would cost digits: Taylor
+        // series of tanh(s)/s in s^2 there (first omitted term < 2e-18)
         const double e2 = fm::exp(-2.0 * s);
-        tt = (s < 0.1) ? tanh(s) : (1.0 - e2) * fm::rcp(1.0 + e2);
+        tt = (1.0 - e2) * fm::rcp(1.0 + e2);
+        if (s < 0.1) {
+            double g = -929569.0 / 638512875.0;
+            g = fma(g, a, 21844.0 / 6081075.0);
+            g = fma(g, a, -1382.0 / 155925.0);
+            g = fma(g, a, 62.0 / 2835.0);
+            g = fma(g, a, -17.0 / 315.0);
+            g = fma(g, a, 2.0 / 15.0);
+            g = fma(g, a, -1.0 / 3.0);
+            tt = s * fma(g, a, 1.0);
+        }
     }
     f = tt * rs;
     double t = (1.0 - f) * inv;

@@ -14,6 +14,7 @@
 // refilled from a per-bucket work counter, found with __ballot_sync/__popc, so a warp never
 // idles on another lane's rejection loop.  Nothing here synchronises the host.
 #include <stdlib.h>
+#include <string.h>
 
 #include "pgm_internal.h"
 #include "pgm_methods.cuh"
@@ -137,200 +138,444 @@ invalid_h(double h, double& value)
 }
 
 // ---------------------------------------------------------------------------------------
-// bucketing pre-pass
+// buckets
 // ---------------------------------------------------------------------------------------
-constexpr int kBucketThreads = 256;
-constexpr int kBucketItems = 8;
-constexpr int kBucketTile = kBucketThreads * kBucketItems;  // elements per block
-constexpr uint8_t kBucketNone = 255;
-
-// bucket ids (also the order of the per-method lists inside the chunk's index list)
-// (the gamma method never needs the pre-pass: it runs on the identity range)
+// bucket ids (the gamma method never needs the tile pass: it runs on the identity range)
 enum : int { kBDevroye = 0, kBAlternate = 1, kBSaddleFull = 2, kBSaddleLeft = 3, kBSaddleFar = 4, kBAlternateLeft = 5,
              kBSaddleMid = 6, kBNormal = 7, kBDevroyeMSH = 8, kNumBuckets = 9, kBGamma = 9 };
+constexpr uint32_t kBucketNone = 15;
 
 // ctl layout (uint32): [0..9] bucket counts, [10..19] record bases, [20..29] work counters, [30] ticket
 constexpr int kCtlCount = 0, kCtlBase = 10, kCtlWork = 20, kCtlTicket = 30, kCtlWords = 32;
 static_assert(kNumBuckets <= 10, "ctl layout");
 
+// (written with selects, not branches: the tile kernel classifies eight elements per thread and the lanes
+// of a warp meet every bucket)
 __host__ __device__ __forceinline__ int
 bucket_of(int method, double h, double z, bool compat)
 {
-    switch (method) {
-        // |z|/2 < 1/T: exponential-pair proposal, else Michael-Schucany-Haas (z = NaN is sampled as z = 0)
-        case kDevroye: return (0.5 * fabs(z) >= 1.5625) ? kBDevroyeMSH : kBDevroye;
-        case kAlternate: return alternate_left_only(z) ? kBAlternateLeft : kBAlternate;
-        case kSaddle: {
-            // the far kernel's buckets: |z| >= 14 (proposals below x = 0.2 almost surely: closed-form
-            // solve for every lane) and 8 <= |z| < 14 (a mix of closed-form and iterative solves)
-            int sm = saddle_mode(h, z, compat);
-            return sm == kSaddleFull ? kBSaddleFull : sm == kSaddleLeft ? kBSaddleLeft
-                   : fabs(z) >= 14.0 ? kBSaddleFar : kBSaddleMid;
-        }
-        case kNormal: return kBNormal;
-        default: return kBGamma;
-    }
+    const double az = fabs(z);  // (z = NaN fails every test below: it is sampled as z = 0)
+    // |z|/2 < 1/T: exponential-pair proposal, else Michael-Schucany-Haas
+    const int bd = (0.5 * az >= 1.5625) ? kBDevroyeMSH : kBDevroye;
+    const int ba = alternate_left_only(z) ? kBAlternateLeft : kBAlternate;
+    // the far kernel's buckets: |z| >= 14 (proposals below x = 0.2 almost surely: closed-form solve for every
+    // lane) and 8 <= |z| < 14 (a mix of closed-form and iterative solves)
+    const int sm = saddle_mode(h, z, compat);
+    const int bs = sm == kSaddleFull ? kBSaddleFull : sm == kSaddleLeft ? kBSaddleLeft
+                   : az >= 14.0 ? kBSaddleFar : kBSaddleMid;
+    return method == kNormal ? kBNormal : method == kSaddle ? bs : method == kDevroye ? bd
+           : method == kAlternate ? ba : kBGamma;
 }
 
-// Layout of the pre-pass: a block owns kTilesPerBlock consecutive tiles of kBucketTile elements;
-// thread t of a tile owns the 8 CONSECUTIVE elements tile*2048 + t*8 .. +7, so h and z are read
-// with 16-byte loads and the 8 bucket ids are stored as one 8-byte word.  Per-bucket counts travel
-// packed two to a 32-bit word (16 bits each; a block holds kTilesPerBlock * 2048 <= 8192 elements).
-// Measured on cfg4 (ms per 1e9 elements): 1 tile 5.13, 2 tiles 4.64, 4 tiles 4.87, 8 tiles 8.9.
-constexpr int kTilesPerBlock = 2;
-constexpr int kPacked = (kNumBuckets + 1) / 2;
+// Where a bucket's elements are drawn.  The near-dense, short-setup buckets (normal approximation,
+// far saddle, both devroye proposals: 91 % of cfg4, all of cfg2) are drawn INSIDE tile_kernel, from
+// shared memory, and their outputs leave the SM as part of the tile's coalesced store.  The divergent
+// buckets go to global element lists: slot s of the pass's ElemLists holds (index, h, z) of its
+// elements, compacted, so the per-method kernels read contiguously instead of gathering 8-byte
+// operands through 32-byte sectors.
+__host__ __device__ __forceinline__ int
+list_slot(int bucket)
+{
+    switch (bucket) {
+        case kBAlternate: return 0;
+        case kBSaddleFull: return 1;
+        case kBSaddleLeft: return 2;
+        case kBAlternateLeft: return 3;
+        case kBSaddleMid: return 4;
+        default: return -1;  // drawn in the tile
+    }
+}
+constexpr int kNumListSlots = 5;
 
+struct ElemLists {
+    uint32_t* idx;  // slot s: idx + s * stride, h + s * stride, z + s * stride
+    double* h;
+    double* z;
+    uint32_t stride;
+};
+
+// ---------------------------------------------------------------------------------------
+// work description shared by the per-method kernels
+// ---------------------------------------------------------------------------------------
+// A bucket is either the identity range [0, count_imm) of the chunk (ctl == nullptr; operands come
+// from FillArgs) or one slot of the pass's element lists, whose length and record base live in ctl
+// on the device.
+struct Bucket {
+    const uint32_t* idx;  // list mode: element indices (relative to a.base); nullptr: identity range
+    const double* lh;     // list mode: the elements' h and z, compacted in list order
+    const double* lz;
+    const uint32_t* ctl;
+    int bucket;
+    uint32_t count_imm;
+    double* params;  // record storage for this chunk (kMaxRecordFields doubles per element)
+    int uniform;     // 1: one record (position 0) serves every element (scalar h and z)
+};
+
+struct BucketView {
+    const uint32_t* idx;
+    uint32_t count;
+    double* recs;     // field f of position p at recs[f * stride + p]
+    uint32_t stride;
+};
+
+__device__ __forceinline__ BucketView
+view_of(const Bucket& b)
+{
+    BucketView v;
+    v.idx = b.idx;
+    v.count = b.count_imm;
+    v.recs = b.params;
+    if (b.ctl) {
+        uint32_t base = b.ctl[kCtlBase + b.bucket];
+        v.count = b.ctl[kCtlCount + b.bucket];
+        v.recs = b.params + (size_t)base * kMaxRecordFields;
+    }
+    v.stride = b.uniform ? 1u : v.count;
+    return v;
+}
+
+// operands of list position pos (list mode) or of element e (identity range)
 __device__ __forceinline__ void
-packed_add(uint32_t (&pc)[kPacked], int bucket)
+bucket_operands(const FillArgs& a, const Bucket& b, uint32_t pos, uint32_t& e, double& h, double& z)
 {
-#pragma unroll
-    for (int w = 0; w < kPacked; ++w) {
-        pc[w] += (bucket == 2 * w) ? 1u : (bucket == 2 * w + 1) ? 0x10000u : 0u;
+    if (b.idx) {
+        e = b.idx[pos];
+        h = b.lh[pos];
+        z = b.lz[pos];
+    }
+    else {
+        e = pos;
+        load_hz(a, a.base + e, h, z);
     }
 }
 
-__device__ __forceinline__ uint32_t
-packed_get(const uint32_t (&pc)[kPacked], int q)
+struct RecView {
+    const double* base;
+    uint32_t stride, pos;
+    __device__ __forceinline__ double operator[](int f) const { return base[(size_t)f * stride + pos]; }
+};
+
+// FUSED sampling: the lane computes its element's record itself at refill (registers only) instead of
+// reading what setup_kernel stored.
+struct LocalRec {
+    const double* v;
+    __device__ __forceinline__ double operator[](int f) const { return v[f]; }
+};
+
+// ---------------------------------------------------------------------------------------
+// tile kernel: classify + draw the dense buckets in shared memory + compact the rest
+// ---------------------------------------------------------------------------------------
+// One block owns one tile of kTile consecutive elements:
+//   1. h and z are read ONCE, with 16-byte coalesced loads, into shared memory; every element gets its
+//      bucket (invalid h: the NaN / inf of src/pgm_random.c:137-141 goes straight to the output tile);
+//   2. per-bucket local index lists are built in shared memory (MATCH.ANY groups the lanes of a bucket,
+//      one shared-memory atomic per group);
+//   3. the elements of the divergent buckets are appended, as (index, h, z), to the pass's global lists
+//      (one global atomic per bucket and block reserves the range; stores are contiguous per bucket);
+//   4. the in-tile buckets are drawn from shared memory: the normal approximation densely, two elements
+//      per thread and trip; far saddle and devroye by warps of persistent lanes that retire finished
+//      elements and refill from the tile's list (__ballot_sync/__popc), exactly as sample_kernel does
+//      on a global list;
+//   5. the tile's outputs leave as one coalesced, 16-byte vectorised store.  Positions that belong to a
+//      divergent bucket carry NaN until that bucket's kernel, later in stream order, overwrites them.
+// HBM traffic: 16 B in + 8 B out per element, + 20 B written for each element of a divergent bucket.
+// Which lane draws an element never changes the draw (private Philox stream per element).
+constexpr int kTileThreads = 256;
+constexpr int kTileItems = 8;
+constexpr int kTile = kTileThreads * kTileItems;
+#ifndef PGM_TILE_BLOCKS_PER_SM
+#define PGM_TILE_BLOCKS_PER_SM 4
+#endif
+
+// One batch of up to 32 far-saddle elements of a tile, drawn to completion by one warp (1.004 proposals
+// per sample: a refill loop would have nothing to refill from).
+__device__ __forceinline__ void
+tile_far_batch(const FillArgs& a, bool compat, uint64_t index0, const uint16_t* __restrict__ list, uint32_t count,
+               uint32_t first, const double* s_z, double* s_hout, uint32_t lane)
 {
-    return (q & 1) ? (pc[q >> 1] >> 16) : (pc[q >> 1] & 0xffffu);
+    using M = SaddleFar;
+    const uint32_t pos = first + lane;
+    bool active = pos < count;
+    M::Par par;
+    M::State st;
+    M::Rng rng;
+    uint32_t e = 0;
+    if (active) {
+        e = list[pos];
+        double loc[M::kFields];
+        M::make_record(s_hout[e], s_z[e], compat, loc);
+        M::load(LocalRec{loc}, par, st, compat);
+        rng.init(a.key, index0 + e);
+    }
+    while (__any_sync(0xffffffffu, active)) {
+        if (active && M::step(par, st, rng, compat)) {
+            s_hout[e] = st.acc;
+            active = false;
+        }
+    }
 }
 
-// One pass builds the per-method element lists.  Phase 1: every thread classifies its 8 elements of
-// each of the block's tiles (all loads of the block are in flight together) and stores the 8 bucket
-// ids as one 64-bit word in shared memory.  The block's per-bucket totals then reserve a
-// range of each bucket's list with ONE atomicAdd per bucket and block (ctl[kCtlCount + q] ends up as
-// the bucket's length).  Phase 2 re-reads the ids from shared memory in striped order and writes the
-// element indices.  Bucket q's list is list + q * list_stride; the order of the entries inside a
-// block's range and of the blocks' ranges depends on scheduling, which changes which lane draws an
-// element, never what is drawn (private Philox stream per element).
-// The last block to finish (ticket counter, no spinning) turns the totals into the record bases.
+// persistent lanes over one in-tile list (same loop as sample_kernel, work counter in shared memory)
+template <class M>
+__device__ __forceinline__ void
+tile_sample(const FillArgs& a, bool compat, uint64_t index0, const uint16_t* __restrict__ list, uint32_t count,
+            uint32_t* s_next, const double* s_z, double* s_hout, uint32_t lane, uint32_t lt)
+{
+    if (count == 0) return;  // block-uniform
+    typename M::Par par;
+    typename M::State st;
+    typename M::Rng rng;
+    uint32_t e = 0;
+    bool active = false;
+    uint32_t wnext = 0, wend = 0;
+    bool exhausted = false;
+    for (;;) {
+        const uint32_t need = __ballot_sync(0xffffffffu, !active);
+        if (need != 0 && !(exhausted && wnext == wend)) {
+            if (wnext == wend) {
+                uint32_t w = 0;
+                if (lane == 0) w = atomicAdd(s_next, 32u);
+                w = __shfl_sync(0xffffffffu, w, 0);
+                if (w >= count) {
+                    exhausted = true;
+                }
+                else {
+                    wnext = w;
+                    wend = min(w + 32u, count);
+                }
+            }
+            if (wnext < wend) {
+                const uint32_t pos = wnext + __popc(need & lt);
+                if (!active && pos < wend) {
+                    e = list[pos];
+                    double loc[M::kFields];
+                    M::make_record(s_hout[e], s_z[e], compat, loc);
+                    if (M::load(LocalRec{loc}, par, st, compat)) {
+                        rng.init(a.key, index0 + e);
+                        active = true;
+                    }
+                    else {
+                        s_hout[e] = 0.0;  // nothing to draw (devroye with floor(h) == 0)
+                    }
+                }
+                wnext = min(wnext + (uint32_t)__popc(need), wend);
+            }
+        }
+        if (active) {
+            if (M::step(par, st, rng, compat)) {
+                s_hout[e] = st.acc;
+                active = false;
+            }
+        }
+        if (exhausted && wnext == wend && !__any_sync(0xffffffffu, active)) break;
+    }
+}
+
 // `method` is the requested sampler (kHybrid: src/pgm_random.c:105-121 decides per element).
 // VEC: h and z are contiguous, 16-byte aligned arrays (or scalars).
 template <bool VEC>
-__global__ void __launch_bounds__(kBucketThreads)
-bucket_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, uint32_t* __restrict__ list,
-              uint32_t list_stride)
+__global__ void __launch_bounds__(kTileThreads, PGM_TILE_BLOCKS_PER_SM)
+tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, ElemLists el, uint32_t tile_first,
+            uint32_t tiles_total)
 {
-    __shared__ uint32_t s_cnt[kPacked];
-    __shared__ uint32_t s_run[kNumBuckets];  // next free list slot of each bucket for this block
-    __shared__ __align__(8) uint8_t s_meth[kTilesPerBlock][kBucketTile];
-    const uint32_t lane = threadIdx.x & 31;
-    if (threadIdx.x < kPacked) s_cnt[threadIdx.x] = 0;
-    __syncthreads();
+    // s_hout: h on the way in, the tile's outputs on the way out (an element's h is consumed by the
+    // thread that later writes its output)
+    __shared__ __align__(16) double s_hout[kTile];
+    __shared__ __align__(16) double s_z[kTile];
+    __shared__ uint16_t s_list[kTile];         // local indices, grouped by bucket
+    __shared__ uint32_t s_cnt[kNumBuckets];    // elements of each bucket in this tile
+    __shared__ uint32_t s_off[kNumBuckets];    // start of each bucket's group in s_list
+    __shared__ uint32_t s_gbase[kNumBuckets];  // list buckets: start of this tile's range in the global list
+    __shared__ uint32_t s_next[kNumBuckets];   // in-tile buckets: work counter
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t tile0 = (tile_first + blockIdx.x) * kTile;  // first element of the tile inside the pass
+    const uint32_t tn = VEC ? (uint32_t)kTile : min((uint32_t)kTile, n - tile0);
+    const uint64_t g0 = a.base + tile0;
     const bool compat = a.compat != 0;
-    uint32_t pc[kPacked];
+    if (tid < kNumBuckets) {
+        s_cnt[tid] = 0;
+        s_next[tid] = 0;
+    }
+    __syncthreads();
+
+    // ---- 1. load + classify.  Thread t owns local elements j * 512 + 2 t + {0, 1}, j = 0..3 ----
+    uint32_t where[kTileItems / 2] = {0, 0, 0, 0};  // per owned element: bucket (4 bits) | position in its group (12 bits)
+    {
+        double hv[kTileItems], zv[kTileItems];
+        if (VEC) {
+            if (a.h) {
+                const double2* p = reinterpret_cast<const double2*>(a.h + g0);
 #pragma unroll
-    for (int w = 0; w < kPacked; ++w) pc[w] = 0;
-#pragma unroll
-    for (int tile = 0; tile < kTilesPerBlock; ++tile) {
-        const uint32_t e0 = (blockIdx.x * kTilesPerBlock + tile) * kBucketTile + threadIdx.x * kBucketItems;
-        uint64_t word = ~0ull;  // kBucketNone in every slot
-        if (e0 < n) {
-            const bool full = (e0 + kBucketItems <= n);
-            auto classify_one = [&](int k, double h, double z) {
-                uint32_t b = kBucketNone;
-                double bad;
-                if (invalid_h(h, bad)) {
-                    a.out[a.base + e0 + k] = bad;
+                for (int j = 0; j < kTileItems / 2; ++j) {
+                    const double2 v = __ldg(p + j * kTileThreads + tid);
+                    hv[2 * j] = v.x;
+                    hv[2 * j + 1] = v.y;
                 }
-                else {
-                    int m = (method == kHybrid) ? hybrid_select(h, z) : method;
-                    b = (uint32_t)bucket_of(m, h, z, compat);
-                    packed_add(pc, (int)b);
-                }
-                word = (word & ~(0xffull << (8 * k))) | ((uint64_t)b << (8 * k));
-            };
-            if (VEC && full) {
-                double hv[kBucketItems], zv[kBucketItems];
-                const uint64_t g0 = a.base + e0;
-                if (a.h) {
-                    const double2* p = reinterpret_cast<const double2*>(a.h + g0);
-#pragma unroll
-                    for (int k = 0; k < kBucketItems / 2; ++k) {
-                        double2 v = __ldg(p + k);
-                        hv[2 * k] = v.x;
-                        hv[2 * k + 1] = v.y;
-                    }
-                }
-                else {
-#pragma unroll
-                    for (int k = 0; k < kBucketItems; ++k) hv[k] = a.h_scalar;
-                }
-                if (a.z) {
-                    const double2* p = reinterpret_cast<const double2*>(a.z + g0);
-#pragma unroll
-                    for (int k = 0; k < kBucketItems / 2; ++k) {
-                        double2 v = __ldg(p + k);
-                        zv[2 * k] = v.x;
-                        zv[2 * k + 1] = v.y;
-                    }
-                }
-                else {
-#pragma unroll
-                    for (int k = 0; k < kBucketItems; ++k) zv[k] = a.z_scalar;
-                }
-#pragma unroll
-                for (int k = 0; k < kBucketItems; ++k) classify_one(k, hv[k], zv[k]);
             }
             else {
+#pragma unroll
+                for (int k = 0; k < kTileItems; ++k) hv[k] = a.h_scalar;
+            }
+            if (a.z) {
+                const double2* p = reinterpret_cast<const double2*>(a.z + g0);
+#pragma unroll
+                for (int j = 0; j < kTileItems / 2; ++j) {
+                    const double2 v = __ldg(p + j * kTileThreads + tid);
+                    zv[2 * j] = v.x;
+                    zv[2 * j + 1] = v.y;
+                }
+            }
+            else {
+#pragma unroll
+                for (int k = 0; k < kTileItems; ++k) zv[k] = a.z_scalar;
+            }
+        }
+        else {
+            // partial tile, or strided / broadcast / unaligned operands: staged through shared memory (one
+            // copy of the general index arithmetic)
 #pragma unroll 1
-                for (int k = 0; k < kBucketItems; ++k) {
-                    if (e0 + k < n) {
-                        double h, z;
-                        load_hz(a, a.base + e0 + k, h, z);
-                        classify_one(k, h, z);
-                    }
+            for (int k = 0; k < kTileItems; ++k) {
+                const uint32_t e = (k >> 1) * (2 * kTileThreads) + 2 * tid + (k & 1);
+                double h = 1.0, z = 0.0;
+                if (e < tn) load_hz(a, g0 + e, h, z);
+                s_hout[e] = h;
+                s_z[e] = z;
+            }
+#pragma unroll
+            for (int j = 0; j < kTileItems / 2; ++j) {
+                const double2 vh = reinterpret_cast<const double2*>(s_hout)[j * kTileThreads + tid];
+                const double2 vz = reinterpret_cast<const double2*>(s_z)[j * kTileThreads + tid];
+                hv[2 * j] = vh.x;
+                hv[2 * j + 1] = vh.y;
+                zv[2 * j] = vz.x;
+                zv[2 * j + 1] = vz.y;
+            }
+        }
+        // Bucket of each element, and its position inside the tile's group of that bucket: the lanes of a
+        // bucket are found with one MATCH.ANY on the bucket id, the lowest lane of a group takes the group's
+        // positions from the bucket's counter in shared memory.
+#pragma unroll
+        for (int k = 0; k < kTileItems; ++k) {
+            const uint32_t e = (k >> 1) * (2 * kTileThreads) + 2 * tid + (k & 1);
+            double hk = hv[k], bad;
+            const bool inval = invalid_h(hk, bad);
+            const int m = (method == kHybrid) ? hybrid_select(hk, zv[k]) : method;
+            const uint32_t b = (e < tn && !inval) ? (uint32_t)bucket_of(m, hk, zv[k], compat) : kBucketNone;
+            hv[k] = inval ? bad : hk;  // invalid h: the output of this element
+            const bool valid = b != kBucketNone;
+            const uint32_t same = __match_any_sync(0xffffffffu, b);
+            const int leader = __ffs(same) - 1;
+            uint32_t r = 0;
+            if (valid && (int)lane == leader) r = atomicAdd(&s_cnt[b], (uint32_t)__popc(same));
+            r = __shfl_sync(0xffffffffu, r, leader) + __popc(same & lt);
+            where[k >> 1] |= (b | (r << 4)) << (16 * (k & 1));
+        }
+#pragma unroll
+        for (int j = 0; j < kTileItems / 2; ++j) {
+            reinterpret_cast<double2*>(s_hout)[j * kTileThreads + tid] = make_double2(hv[2 * j], hv[2 * j + 1]);
+            reinterpret_cast<double2*>(s_z)[j * kTileThreads + tid] = make_double2(zv[2 * j], zv[2 * j + 1]);
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. group offsets; reserve the tile's range in each global list; write the local lists ----
+    if (tid < kNumBuckets) {
+        uint32_t off = 0;
+        for (uint32_t q = 0; q < tid; ++q) off += s_cnt[q];
+        s_off[tid] = off;
+        const uint32_t c = s_cnt[tid];
+        uint32_t base = 0;
+        if (c != 0 && list_slot((int)tid) >= 0) base = atomicAdd(&ctl[kCtlCount + tid], c);
+        s_gbase[tid] = base;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kTileItems; ++k) {
+        const uint32_t e = (k >> 1) * (2 * kTileThreads) + 2 * tid + (k & 1);
+        const uint32_t w = (where[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+        const uint32_t q = w & 15u;
+        if (q != kBucketNone) s_list[s_off[q] + (w >> 4)] = (uint16_t)e;
+    }
+    __syncthreads();
+
+    // ---- 3. divergent buckets: append (index, h, z) to the global lists ----
+#pragma unroll 1
+    for (int q = 0; q < kNumBuckets; ++q) {
+        const int slot = list_slot(q);
+        if (slot < 0) continue;
+        const uint32_t c = s_cnt[q];
+        if (c == 0) continue;  // block-uniform
+        const uint32_t off = s_off[q];
+        const size_t dst = (size_t)slot * el.stride + s_gbase[q];
+        for (uint32_t i = tid; i < c; i += kTileThreads) {
+            const uint32_t e = s_list[off + i];
+            el.idx[dst + i] = tile0 + e;
+            el.h[dst + i] = s_hout[e];
+            el.z[dst + i] = s_z[e];
+            s_hout[e] = NAN;  // pending: written by the bucket's own kernel
+        }
+    }
+
+    // ---- 4. in-tile buckets ----
+    // Far saddle and normal approximation: one work queue per tile.  Items 0 .. nfar-1 are batches of 32
+    // far-saddle elements (the expensive ones first), the rest batches of 64 normal-approximation elements
+    // (two per lane: their dependency chains interleave); a warp takes the next item when it is done with its
+    // last, so the warps of the block reach the barrier below within one item of each other.
+    {
+        const uint64_t index0 = a.first_index + g0;
+        const uint32_t cf = s_cnt[kBSaddleFar], cn = s_cnt[kBNormal];
+        const uint16_t* lf = s_list + s_off[kBSaddleFar];
+        const uint16_t* ln = s_list + s_off[kBNormal];
+        const uint32_t nfar = (cf + 31u) >> 5, nitems = nfar + ((cn + 63u) >> 6);
+        for (;;) {
+            uint32_t it = 0;
+            if (lane == 0) it = atomicAdd(&s_next[kBNormal], 1u);
+            it = __shfl_sync(0xffffffffu, it, 0);
+            if (it >= nitems) break;
+            if (it < nfar) {
+                tile_far_batch(a, compat, index0, lf, cf, it << 5, s_z, s_hout, lane);
+            }
+            else {
+                const uint32_t i = ((it - nfar) << 6) + lane;
+                if (i < cn) {
+                    const bool two = i + 32u < cn;
+                    const uint32_t e0 = ln[i], e1 = two ? ln[i + 32u] : e0;
+                    RngInlineRK r0, r1;
+                    r0.init(a.key, index0 + e0);
+                    r1.init(a.key, index0 + e1);
+                    const double v0 = normal_approx_sample(r0, s_hout[e0], s_z[e0]);
+                    const double v1 = normal_approx_sample(r1, s_hout[e1], s_z[e1]);
+                    if (two) s_hout[e1] = v1;
+                    s_hout[e0] = v0;
                 }
             }
         }
-        *reinterpret_cast<uint64_t*>(&s_meth[tile][threadIdx.x * kBucketItems]) = word;
-    }
-    // block totals -> one reservation per bucket
-#pragma unroll
-    for (int w = 0; w < kPacked; ++w) {
-        // a thread holds at most 8 * kTilesPerBlock <= 32 elements, a warp 1024: the packed 16-bit sums
-        // cannot carry
-        for (int off = 16; off > 0; off >>= 1) pc[w] += __shfl_xor_sync(0xffffffffu, pc[w], off);
-    }
-    if (lane == 0) {
-#pragma unroll
-        for (int w = 0; w < kPacked; ++w) atomicAdd(&s_cnt[w], pc[w]);
+        tile_sample<DevroyeT<kDevroyePair>>(a, compat, index0, s_list + s_off[kBDevroye], s_cnt[kBDevroye],
+                                            &s_next[kBDevroye], s_z, s_hout, lane, lt);
+        tile_sample<DevroyeT<kDevroyeMSH>>(a, compat, index0, s_list + s_off[kBDevroyeMSH], s_cnt[kBDevroyeMSH],
+                                           &s_next[kBDevroyeMSH], s_z, s_hout, lane, lt);
     }
     __syncthreads();
-    if (threadIdx.x < kNumBuckets) {
-        uint32_t v = s_cnt[threadIdx.x >> 1];
-        v = (threadIdx.x & 1) ? (v >> 16) : (v & 0xffffu);
-        const uint32_t base = v ? atomicAdd(&ctl[kCtlCount + threadIdx.x], v) : 0u;
-        s_run[threadIdx.x] = threadIdx.x * list_stride + base;
-    }
-    __syncthreads();  // s_run and s_meth are visible
-    // Phase 2, striped: lane t of stripe j takes element t0 + 256 j + t, so the lanes of a warp that
-    // share a bucket are consecutive elements and get consecutive list slots (coalesced stores).
-    // The lanes of each bucket are found with one MATCH.ANY on the bucket id; the lowest lane of a
-    // group reserves the group's slots from the block's running counter.
-    const uint32_t lt = (1u << lane) - 1u;
+
+    // ---- 5. the tile's outputs ----
+    double* out = a.out + g0;
+    if (tn == kTile && ((uintptr_t)out & 15) == 0) {
 #pragma unroll
-    for (int tile = 0; tile < kTilesPerBlock; ++tile) {
-        const uint32_t t0 = (blockIdx.x * kTilesPerBlock + tile) * kBucketTile;
-        if (t0 >= n) break;  // block-uniform
-#pragma unroll
-        for (int j = 0; j < kBucketItems; ++j) {
-            const uint32_t i = j * kBucketThreads + threadIdx.x;
-            const uint32_t q = s_meth[tile][i];
-            const bool valid = q < (uint32_t)kNumBuckets;
-            const uint32_t same = __match_any_sync(0xffffffffu, q);
-            const int leader = __ffs(same) - 1;
-            uint32_t slot = 0;
-            if (valid && (int)lane == leader) slot = atomicAdd(&s_run[q], (uint32_t)__popc(same));
-            slot = __shfl_sync(0xffffffffu, slot, leader < 0 ? 0 : leader);
-            if (valid) list[slot + __popc(same & lt)] = t0 + i;
+        for (int j = 0; j < kTileItems / 2; ++j) {
+            reinterpret_cast<double2*>(out)[j * kTileThreads + tid] = reinterpret_cast<const double2*>(s_hout)[j * kTileThreads + tid];
         }
     }
+    else {
+        for (uint32_t e = tid; e < tn; e += kTileThreads) out[e] = s_hout[e];
+    }
+
     // the last block turns the bucket totals into the bases of the packed record regions
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         __threadfence();
         const uint32_t ticket = atomicAdd(&ctl[kCtlTicket], 1u);
-        if (ticket == gridDim.x - 1) {
+        if (ticket == tiles_total - 1) {
             __threadfence();
             uint32_t base = 0;
             for (int q = 0; q < kNumBuckets; ++q) {
@@ -342,52 +587,6 @@ bucket_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, ui
 }
 
 // ---------------------------------------------------------------------------------------
-// work description shared by the per-method kernels
-// ---------------------------------------------------------------------------------------
-// A bucket is either the identity range [0, count_imm) of the chunk (ctl == nullptr) or the
-// bucket-th list (list + bucket * list_stride), whose length and record base live in ctl on the
-// device.
-struct Bucket {
-    const uint32_t* list;
-    const uint32_t* ctl;
-    int bucket;
-    uint32_t count_imm;
-    uint32_t list_stride;  // bucket q's list starts at list + q * list_stride
-    double* params;  // record storage for this chunk (kMaxRecordFields doubles per element)
-    int uniform;     // 1: one record (position 0) serves every element (scalar h and z)
-};
-
-struct BucketView {
-    const uint32_t* list;
-    uint32_t count;
-    double* recs;     // field f of position p at recs[f * stride + p]
-    uint32_t stride;
-};
-
-__device__ __forceinline__ BucketView
-view_of(const Bucket& b)
-{
-    BucketView v;
-    v.list = b.list;
-    v.count = b.count_imm;
-    v.recs = b.params;
-    if (b.ctl) {
-        uint32_t base = b.ctl[kCtlBase + b.bucket];
-        v.count = b.ctl[kCtlCount + b.bucket];
-        v.list = b.list + (size_t)b.bucket * b.list_stride;
-        v.recs = b.params + (size_t)base * kMaxRecordFields;
-    }
-    v.stride = b.uniform ? 1u : v.count;
-    return v;
-}
-
-struct RecView {
-    const double* base;
-    uint32_t stride, pos;
-    __device__ __forceinline__ double operator[](int f) const { return base[(size_t)f * stride + pos]; }
-};
-
-// ---------------------------------------------------------------------------------------
 // setup kernel: one thread per element, no rejection loops
 // ---------------------------------------------------------------------------------------
 template <class M>
@@ -397,14 +596,13 @@ setup_kernel(FillArgs a, Bucket b)
     const BucketView v = view_of(b);
     const uint32_t nrec = b.uniform ? 1u : v.count;
     for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < nrec; pos += gridDim.x * blockDim.x) {
-        uint32_t e = v.list ? v.list[pos] : pos;
-        uint64_t g = a.base + e;
+        uint32_t e;
         double h, z, bad;
-        load_hz(a, g, h, z);
+        bucket_operands(a, b, pos, e, h, z);
         double rec[M::kFields];
         if (invalid_h(h, bad)) {
-            // only reachable on the identity range (bucket_kernel filters invalid h itself)
-            if (!b.uniform) a.out[g] = bad;
+            // only reachable on the identity range (tile_kernel filters invalid h itself)
+            if (!b.uniform) a.out[a.base + e] = bad;
 #pragma unroll
             for (int f = 0; f < M::kFields; ++f) rec[f] = NAN;
         }
@@ -424,12 +622,7 @@ constexpr uint32_t kWorkBatch = 64;  // elements a warp reserves per atomic
 
 // FUSED: the lane computes its element's record itself at refill (registers only) instead of reading
 // what setup_kernel stored -- for a method whose setup is short and whose lanes all refill on nearly
-// every trip (saddle-far: 1.004 proposals per sample), this saves the record's round trip through
-// HBM and the second gather of (h, z).
-struct LocalRec {
-    const double* v;
-    __device__ __forceinline__ double operator[](int f) const { return v[f]; }
-};
+// every trip, this saves the record's round trip through HBM.
 
 template <class M, bool FUSED = false>
 __global__ void __launch_bounds__(kPersistThreads)
@@ -467,11 +660,11 @@ sample_kernel(FillArgs a, Bucket b, uint32_t* __restrict__ counter)
             if (wnext < wend) {
                 uint32_t pos = wnext + __popc(need & lt);
                 if (!active && pos < wend) {
-                    uint32_t e = v.list ? v.list[pos] : pos;
-                    g = a.base + e;
-                    if (FUSED) {  // (bucketed lists only: invalid h never reaches a list)
+                    if (FUSED) {  // (list buckets only: invalid h never reaches a list)
+                        uint32_t e;
                         double h, z, loc[M::kFields];
-                        load_hz(a, g, h, z);
+                        bucket_operands(a, b, pos, e, h, z);
+                        g = a.base + e;
                         M::make_record(h, z, compat, loc);
                         if (M::load(LocalRec{loc}, par, st, compat)) {
                             rng.init(a.key, a.first_index + g);
@@ -482,6 +675,7 @@ sample_kernel(FillArgs a, Bucket b, uint32_t* __restrict__ counter)
                         }
                     }
                     else {
+                        g = a.base + (v.idx ? v.idx[pos] : pos);
                         RecView rec{v.recs, v.stride, b.uniform ? 0u : pos};
                         double r0 = rec[0];
                         if (r0 == r0) {  // NaN record: invalid h, already written by setup_kernel
@@ -511,70 +705,34 @@ sample_kernel(FillArgs a, Bucket b, uint32_t* __restrict__ counter)
 // ---------------------------------------------------------------------------------------
 // dense kernels: one pass, no outer rejection loop (normal approximation, gamma convolution)
 // ---------------------------------------------------------------------------------------
-#ifndef PGM_NORMAL_PER_TRIP
-#define PGM_NORMAL_PER_TRIP 2
-#endif
-constexpr int kNormalPerTrip = PGM_NORMAL_PER_TRIP;
-
+// Identity range only (scalar parameters, or the gamma method over arrays): the hybrid / saddle / ... fills
+// over arrays draw their normal-approximation elements inside tile_kernel.
 template <int KIND>
 __global__ void __launch_bounds__(256)
 dense_kernel(FillArgs a, Bucket b)
 {
-    const BucketView v = view_of(b);
+    const uint32_t count = b.count_imm;
     const uint32_t stride = gridDim.x * blockDim.x;
     if (KIND == kNormal) {
-        // kNormalPerTrip elements per trip (their dependency chains interleave and the constants of
-        // the polynomial kernels are fetched once per trip), software-pipelined two deep: the list
-        // indices of trip t + 2 and the (h, z) gathers of trip t + 1 are issued before trip t's
-        // arithmetic, so the two dependent memory round trips never sit on the critical path.
-        // Positions past the end are clamped (valid loads, results unused).
-        if (v.count == 0) return;
-        constexpr int E = kNormalPerTrip;
-        const uint32_t last = v.count - 1;
-        auto entry = [&](uint32_t p) -> uint32_t {
-            p = min(p, last);
-            return v.list ? v.list[p] : p;
-        };
-        uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-        uint32_t e[E], nx[E];
-        double h[E], z[E];
-#pragma unroll
-        for (int i = 0; i < E; ++i) {
-            e[i] = entry(pos + i * stride);
-            nx[i] = entry(pos + (E + i) * stride);
-        }
-#pragma unroll
-        for (int i = 0; i < E; ++i) load_hz(a, a.base + e[i], h[i], z[i]);
-        for (; pos < v.count; pos += E * stride) {
-            uint32_t nn[E];
-            double hn[E], zn[E];
-#pragma unroll
-            for (int i = 0; i < E; ++i) nn[i] = entry(pos + (2 * E + i) * stride);
-#pragma unroll
-            for (int i = 0; i < E; ++i) load_hz(a, a.base + nx[i], hn[i], zn[i]);
-            double out[E];
-#pragma unroll
-            for (int i = 0; i < E; ++i) {
-                double bad;
-                RngInlineRK r;
-                r.init(a.key, a.first_index + a.base + e[i]);
-                out[i] = invalid_h(h[i], bad) ? bad : normal_approx_sample(r, h[i], z[i]);
-            }
-#pragma unroll
-            for (int i = 0; i < E; ++i) {
-                if (pos + i * stride < v.count) a.out[a.base + e[i]] = out[i];
-            }
-#pragma unroll
-            for (int i = 0; i < E; ++i) {
-                e[i] = nx[i], nx[i] = nn[i];
-                h[i] = hn[i], z[i] = zn[i];
-            }
+        // two elements per trip: their dependency chains interleave
+        for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < count; pos += 2 * stride) {
+            const bool two = pos + stride < count;
+            const uint64_t ga = a.base + pos, gb = two ? ga + stride : ga;
+            double ha, za, hb, zb, bad;
+            load_hz(a, ga, ha, za);
+            load_hz(a, gb, hb, zb);
+            RngInlineRK ra, rb;
+            ra.init(a.key, a.first_index + ga);
+            rb.init(a.key, a.first_index + gb);
+            const double va = invalid_h(ha, bad) ? bad : normal_approx_sample(ra, ha, za);
+            const double vb = invalid_h(hb, bad) ? bad : normal_approx_sample(rb, hb, zb);
+            a.out[ga] = va;
+            if (two) a.out[gb] = vb;
         }
         return;
     }
-    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < v.count; pos += stride) {
-        uint32_t e = v.list ? v.list[pos] : pos;
-        uint64_t g = a.base + e;
+    for (uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x; pos < count; pos += stride) {
+        uint64_t g = a.base + pos;
         double h, z, bad;
         load_hz(a, g, h, z);
         if (invalid_h(h, bad)) {
@@ -689,50 +847,103 @@ struct DeviceInfo {
     // sampling kernels: devroye, alternate, saddle-full, saddle-left, saddle-far, alternate-left,
     // saddle-mid (the far kernel on its second bucket)
     int blocks_per_sm[7] = {0, 0, 0, 0, 0, 0, 0};
+    int tile_blocks_per_sm = 1;
+    cudaMemPool_t pool = nullptr;  // the library's own stream-ordered scratch pool
+    int init_rc = 0;
 };
 
+static DeviceInfo g_device_cache[64];
+static std::mutex g_device_mutex;  // first calls from several host threads: one fills the entry, the others wait
+
+// One-time, per device: occupancy of the persistent kernels, the saddle starting-point tables (filled by
+// the solver itself on a private stream, which this call waits for -- the library's only host
+// synchronisation on a device-pointer path, and only on the first call) and a PRIVATE memory pool for the
+// stream-ordered scratch (freed blocks stay cached in it; the device's default pool is left alone).
 static DeviceInfo
 device_info()
 {
-    static DeviceInfo cache[64];
-    static std::mutex mu;  // first calls from several host threads: one of them fills the entry, the others wait
     int dev = 0;
     cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(mu);
-    DeviceInfo& d = cache[dev & 63];
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    DeviceInfo& d = g_device_cache[dev & 63];
     if (d.sms == 0) {
         cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[0], sample_kernel<DevroyeT<kDevroyePair>>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[1], sample_kernel<Alternate>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[2], sample_kernel<SaddleFull>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[3], sample_kernel<SaddleLeft>, kPersistThreads, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[4], sample_kernel<SaddleFar>, kPersistThreads, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[5], sample_kernel<AlternateLeft>, kPersistThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[4], sample_kernel<SaddleFar, true>, kPersistThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[5], sample_kernel<AlternateLeft, true>, kPersistThreads, 0);
         d.blocks_per_sm[6] = d.blocks_per_sm[4];
         for (int i = 0; i < 7; ++i) {
             if (d.blocks_per_sm[i] < 1) d.blocks_per_sm[i] = 1;
         }
-        // starting-point tables of the saddle setup (per device, filled by the solver itself)
-        init_guess_tables_kernel<<<(saddle::kGuessN + 127) / 128, 128>>>();
-        cudaDeviceSynchronize();
-        count_launch(1);
-        // stream-ordered scratch: keep freed blocks cached in the pool instead of returning
-        // them to the OS at every synchronisation
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t thr = UINT64_MAX;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.tile_blocks_per_sm, tile_kernel<true>, kTileThreads, 0);
+        if (d.tile_blocks_per_sm < 1) d.tile_blocks_per_sm = 1;
+        cudaStream_t st = nullptr;
+        cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        if (e == cudaSuccess) {
+            init_guess_tables_kernel<<<(saddle::kGuessN + 127) / 128, 128, 0, st>>>();
+            e = cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+            count_launch(1);
         }
+        if (e == cudaSuccess) {
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof(props));
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            e = cudaMemPoolCreate(&d.pool, &props);
+            if (e == cudaSuccess) {
+                uint64_t thr = UINT64_MAX;
+                cudaMemPoolSetAttribute(d.pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+        }
+        d.init_rc = (int)e;
+        if (e != cudaSuccess) (void)cudaGetLastError();
     }
     return d;
 }
 
-// helper streams per device: 0 for the overlapped bucketing pre-pass, 1 and 2 for the small
-// buckets' kernels (they run beside the big buckets' kernels and fill their tails)
+int
+device_init()
+{
+    return device_info().init_rc;
+}
+
+int
+scratch_alloc(void** p, size_t bytes, cudaStream_t s)
+{
+    DeviceInfo d = device_info();
+    if (d.init_rc != 0) return d.init_rc;
+    return (int)cudaMallocFromPoolAsync(p, bytes, d.pool, s);
+}
+
+// returns the cached scratch of the current device to the driver (after a device synchronisation)
+int
+scratch_release()
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    cudaMemPool_t pool = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_device_mutex);
+        pool = g_device_cache[dev & 63].pool;
+    }
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return (int)e;
+    if (pool == nullptr) return 0;
+    return (int)cudaMemPoolTrimTo(pool, 0);
+}
+
+// helper streams per device: the divergent buckets' kernels of a pass run on them, beside the next
+// pass's tile kernel on the caller's stream
 static cudaStream_t
 helper_stream(int which)
 {
-    static cudaStream_t streams[64][3] = {};
+    static cudaStream_t streams[64][2] = {};
     static std::mutex mu;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -753,13 +964,11 @@ grid_for(uint64_t full, uint64_t count_hint, uint32_t threads)
 // setup + persistent sampling of one bucket with method M (which: 0 devroye, 1 alternate,
 // 2 saddle-full, 3 saddle-left, 4 saddle-far, 5 alternate-left, 6 saddle-mid; profiling kinds are
 // kKindDevroye / kKindSetup + which)
-// Which buckets compute their records inside the sampling kernel (measured on cfg4, ms per 1e9,
-// setup + sampling separate -> fused): saddle-far 8.25 -> 6.86, saddle-mid 2.71 -> 2.44, alternate-left
-// 2.04 -> 1.55, devroye (cfg3, per 1e8) 5.23 -> 5.04; saddle-left gets slower (3.83 -> 4.22: its setup is
-// longer and its lanes refill out of step), and the full saddle / alternate setups are the big ones the
-// split exists for.
-constexpr bool kFuseFar = true, kFuseMid = true, kFuseLeft = false, kFuseAltLeft = true;
-constexpr bool kFuseDevroye = true;  // cfg3 devroye 19.1 -> 19.8e9 with the exponential-free setup (slower with the erfc one)
+// Which list buckets compute their records inside the sampling kernel (measured on cfg4 in round 1, ms per
+// 1e9, setup + sampling separate -> fused): saddle-mid 2.71 -> 2.44, alternate-left 2.04 -> 1.55; saddle-left
+// gets slower (3.83 -> 4.22: its setup is longer and its lanes refill out of step), and the full saddle /
+// alternate setups are the big ones the split exists for.
+constexpr bool kFuseMid = true, kFuseLeft = false, kFuseAltLeft = true;
 
 template <class M, bool FUSED = false>
 static void
@@ -789,24 +998,33 @@ launch_dense(const DeviceInfo& d, const FillArgs& a, const Bucket& b, uint64_t c
     count_launch(1);
 }
 
-// Elements per pass through the pipeline.  Bounds the scratch (5 B + one record per element)
-// and keeps list indices in 32 bits.
-// Pass size.  Every kernel of a pass ends with a partially filled last wave, so fewer, larger
-// passes are faster (cfg4 per 1e9 elements: 2^24 66.8 ms, 2^25 55.5, 2^26 50.7, 2^27 48.5 ms);
-// the per-element path needs 5 B + one record of scratch per element of a pass.  It starts at
-// 2^27 elements (or the smallest power of two >= n) and halves the pass while the stream-ordered
-// allocation of the scratch fails.  PGM_CUDA_CHUNK_LOG2 in the environment pins the pass size
-// (tests use it to cross pass seams).
-constexpr int kChunkLog2Min = 20, kChunkLog2Max = 27;
+// Pass size.  A pass is one tile_kernel launch over up to 2^kChunkLog2Max elements plus the kernels of
+// its divergent buckets.  The one-pass compaction cannot know a list's length before it writes, so the
+// scratch holds one worst-case list per slot: 5 x 20 B per element of a pass (twice with two passes in
+// flight) + one record (72 B) per element: 172 / 272 B per element, 5.8 / 9.1 GB at 2^25.  The pass is
+// halved while the stream-ordered allocation fails.  PGM_CUDA_CHUNK_LOG2 in the environment pins the
+// pass size (tests use it to cross pass seams).
+#ifndef PGM_CHUNK_LOG2_MAX
+#define PGM_CHUNK_LOG2_MAX 25
+#endif
+constexpr int kChunkLog2Min = 20, kChunkLog2Max = PGM_CHUNK_LOG2_MAX;
 constexpr uint64_t kSmallMaxDefault = 1ull << 16;  // mixed-method fills break even near 1e5, single-method ones far later
+
+static int
+env_int(const char* name, int lo, int hi, int fallback)
+{
+    const char* e = getenv(name);  // read per call: the tests switch these
+    if (e == nullptr || *e == '\0') return fallback;
+    char* end = nullptr;
+    long v = strtol(e, &end, 10);
+    if (end == e || v < lo || v > hi) return fallback;
+    return (int)v;
+}
 
 static int
 env_chunk_log2()
 {
-    const char* e = getenv("PGM_CUDA_CHUNK_LOG2");
-    if (e == nullptr) return 0;
-    int v = atoi(e);
-    return (v >= 10 && v <= 28) ? v : 0;  // 9 lists x 2^28 entries still index with 32 bits
+    return env_int("PGM_CUDA_CHUNK_LOG2", 11, 28, 0);  // a pass holds at least one tile; 2^28 entries index with 32 bits
 }
 
 static int
@@ -824,21 +1042,24 @@ align256(size_t v)
     return (v + 255) & ~size_t(255);
 }
 
-// largest fill that takes the one-launch path (PGM_CUDA_SMALL_MAX overrides; 0 disables it)
+// largest fill that takes the one-launch path (PGM_CUDA_SMALL_MAX overrides, clamped to 2^22; 0 disables it)
 static uint64_t
 small_max()
 {
-    const char* e = getenv("PGM_CUDA_SMALL_MAX");  // read per call: the tests switch it
-    return e ? (uint64_t)strtoull(e, nullptr, 10) : kSmallMaxDefault;
+    const char* e = getenv("PGM_CUDA_SMALL_MAX");
+    if (e == nullptr || *e == '\0') return kSmallMaxDefault;
+    char* end = nullptr;
+    unsigned long long v = strtoull(e, &end, 10);
+    if (end == e) return kSmallMaxDefault;
+    return v > (1ull << 22) ? (1ull << 22) : (uint64_t)v;
 }
 
-// smallest pass whose buckets are spread over the helper streams (measured: 1e5 mixed elements 251 ->
-// 166 us per call, 1e6: 322 -> 210 us; below 2^16 the one-launch kernel runs instead)
+// smallest pass whose divergent buckets are spread over the helper streams (below 2^16 elements the
+// one-launch kernel runs instead)
 static uint64_t
 multi_min()
 {
-    const char* e = getenv("PGM_CUDA_MULTI_MIN_LOG2");
-    return 1ull << (e ? atoi(e) : 16);
+    return 1ull << env_int("PGM_CUDA_MULTI_MIN_LOG2", 0, 40, 16);
 }
 
 int
@@ -850,6 +1071,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
     if (m < kGamma || m > kHybrid) return -1;
     const bool compat = a.compat != 0;
     DeviceInfo d = device_info();
+    if (d.init_rc != 0) return d.init_rc;
     cudaError_t err;
 
     // with ONE shape for the whole call the elements fall into two or three buckets at most, a warp of
@@ -877,11 +1099,11 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         }
         const int eff = (m == kHybrid) ? hybrid_select(a.h_scalar, a.z_scalar) : m;
         const int bk = bucket_of(eff, a.h_scalar, a.z_scalar, compat);
-        const uint64_t kChunk = 1ull << first_chunk_log2(n);
+        const uint64_t kChunk = 1ull << (env_chunk_log2() ? env_chunk_log2() : 27);
         const uint64_t nchunks = (n + kChunk - 1) / kChunk;
         char* ws = nullptr;
         const size_t rec_bytes = align256(kMaxRecordFields * sizeof(double));
-        if ((err = cudaMallocAsync(&ws, rec_bytes + nchunks * sizeof(uint32_t), s)) != cudaSuccess) return (int)err;
+        if ((err = (cudaError_t)scratch_alloc((void**)&ws, rec_bytes + nchunks * sizeof(uint32_t), s)) != cudaSuccess) return (int)err;
         double* params = (double*)ws;
         uint32_t* counters = (uint32_t*)(ws + rec_bytes);
         cudaMemsetAsync(counters, 0, nchunks * sizeof(uint32_t), s);
@@ -890,7 +1112,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
             const uint64_t off = c * kChunk;
             const uint32_t cn = (uint32_t)((n - off) < kChunk ? (n - off) : kChunk);
             a.base = base0 + off;
-            Bucket b{nullptr, nullptr, bk, cn, 0, params, 1};
+            Bucket b{nullptr, nullptr, nullptr, nullptr, bk, cn, params, 1};
             switch (bk) {
                 case kBDevroye: launch_method<DevroyeT<kDevroyePair>>(d, 0, a, b, cn, counters + c, s); break;
                 case kBDevroyeMSH: launch_method<DevroyeT<kDevroyeMSH>>(d, 0, a, b, cn, counters + c, s); break;
@@ -908,131 +1130,125 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         return (int)cudaGetLastError();
     }
 
-    // per-element parameters (fill2).  hybrid, saddle, alternate and devroye go through the bucketing
-    // pre-pass (they split into specialised kernels); gamma runs on the identity range.
-    const bool bucketed = (m == kHybrid || m == kSaddle || m == kAlternate || m == kDevroye);
+    if (m == kGamma) {
+        // 200 gamma draws per element, no per-element setup worth splitting off: identity range, no scratch
+        const uint64_t chunk = 1ull << 27;
+        const uint64_t base0 = a.base;
+        for (uint64_t off = 0; off < n; off += chunk) {
+            const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
+            a.base = base0 + off;
+            Bucket b{nullptr, nullptr, nullptr, nullptr, kBGamma, cn, nullptr, 0};
+            launch_dense<kGamma>(d, a, b, cn, s);
+        }
+        return (int)cudaGetLastError();
+    }
+
+    // per-element parameters (fill2), every other method: passes of tile_kernel + the divergent buckets'
+    // kernels.  With several passes the divergent buckets of pass k (helper streams) run beside the tile
+    // kernel of pass k + 1 (caller's stream); the element lists are double-buffered, the records are not
+    // (the bucket kernels of pass k + 1 wait for all of pass k's).
     int lg = first_chunk_log2(n);
-    // With several passes the bucketing of pass k+1 (HBM- and issue-bound) runs on a helper stream
-    // while the sampling kernels of pass k (FP64-bound) run on the caller's stream; the bucketing
-    // scratch is double-buffered, the records are not (setup and sampling are serialised on the
-    // caller's stream).
-    const bool overlap = bucketed && n > (1ull << lg) && getenv("PGM_CUDA_NO_OVERLAP") == nullptr;
-    const int nprep = overlap ? 2 : 1;
+    const bool no_overlap = getenv("PGM_CUDA_NO_OVERLAP") != nullptr;
     uint64_t chunk = 0;
     size_t list_bytes = 0, par_bytes = 0, prep_bytes = 0;
     uint32_t list_stride = 0;
+    int nprep = 1;
     const size_t ctl_bytes = align256(kCtlWords * sizeof(uint32_t));
     char* ws = nullptr;
     for (;;) {
         chunk = 1ull << lg;
         const uint64_t cmax = n < chunk ? n : chunk;
-        // one worst-case list per bucket (the single-pass bucketing cannot know the bucket sizes
-        // before it writes): 32 B of scratch per element next to the 72 B of records
+        nprep = (n > chunk && !no_overlap) ? 2 : 1;
         list_stride = (uint32_t)((cmax + 63) & ~uint64_t(63));
-        list_bytes = bucketed ? align256((size_t)list_stride * kNumBuckets * sizeof(uint32_t)) : 0;
-        par_bytes = (m == kGamma) ? 0 : align256(cmax * kMaxRecordFields * sizeof(double));
+        list_bytes = align256((size_t)list_stride * kNumListSlots * (sizeof(uint32_t) + 2 * sizeof(double)));
+        par_bytes = align256(cmax * kMaxRecordFields * sizeof(double));
         prep_bytes = list_bytes + ctl_bytes;
-        err = cudaMallocAsync(&ws, nprep * prep_bytes + par_bytes, s);
+        err = (cudaError_t)scratch_alloc((void**)&ws, nprep * prep_bytes + par_bytes, s);
         if (err == cudaSuccess) break;
         (void)cudaGetLastError();  // clear the sticky-free allocation error and retry smaller
         if (err != cudaErrorMemoryAllocation || lg <= kChunkLog2Min || env_chunk_log2()) return (int)err;
         --lg;
     }
     struct Prep {
-        uint32_t *list, *ctl;
+        ElemLists el;
+        uint32_t* ctl;
     } prep[2];
     for (int i = 0; i < nprep; ++i) {
         char* base = ws + (size_t)i * prep_bytes;
-        prep[i].list = (uint32_t*)base;
+        // h and z first (8-byte aligned whatever the stride), then the indices
+        prep[i].el.h = (double*)base;
+        prep[i].el.z = prep[i].el.h + (size_t)list_stride * kNumListSlots;
+        prep[i].el.idx = (uint32_t*)(prep[i].el.z + (size_t)list_stride * kNumListSlots);
+        prep[i].el.stride = list_stride;
         prep[i].ctl = (uint32_t*)(base + list_bytes);
     }
     if (nprep == 1) prep[1] = prep[0];
     double* params = (double*)(ws + (size_t)nprep * prep_bytes);
     const uint64_t cmax_elems = n < chunk ? n : chunk;
 
-    // 16-byte loads in the pre-pass need contiguous, aligned operands (a scalar operand is fine)
+    // 16-byte loads in the tile kernel need contiguous, aligned operands (a scalar operand is fine)
     const bool vec = a.bc.ndim == 0 && (a.h == nullptr || (a.h_stride == 1 && ((uintptr_t)(a.h + a.base) & 15) == 0)) &&
                      (a.z == nullptr || (a.z_stride == 1 && ((uintptr_t)(a.z + a.base) & 15) == 0));
     const uint64_t base0 = a.base;
 
-    if (!bucketed) {
-        uint32_t* ctl = prep[0].ctl;
-        for (uint64_t off = 0; off < n; off += chunk) {
-            const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
-            a.base = base0 + off;
-            cudaMemsetAsync(ctl, 0, ctl_bytes, s);
-            Bucket b{nullptr, nullptr, 0, cn, 0, params, 0};
-            launch_dense<kGamma>(d, a, b, cn, s);
-        }
-        cudaFreeAsync(ws, s);
-        return (int)cudaGetLastError();
-    }
-
-    // bucketing pre-pass of one pass, on stream `sb`, into scratch set `pp`
-    auto bucketing = [&](const FillArgs& ap, uint32_t cn, const Prep& pp, cudaStream_t sb) {
-        const uint32_t nblocks = (cn + kBucketTile * kTilesPerBlock - 1) / (kBucketTile * kTilesPerBlock);
-        cudaMemsetAsync(pp.ctl, 0, ctl_bytes, sb);
+    auto tile_pass = [&](const FillArgs& ap, uint32_t cn, const Prep& pp, cudaStream_t st) {
+        const uint32_t nblocks = (cn + kTile - 1) / kTile;
+        // full tiles of contiguous, aligned operands take the 16-byte-load kernel; a trailing partial tile
+        // (or every tile, for general operands) the general one
+        const uint32_t nvec = vec ? cn / kTile : 0;
+        cudaMemsetAsync(pp.ctl, 0, ctl_bytes, st);
         {
-            ScopedKernelTimer timer(kKindClassify, sb);
-            if (vec) bucket_kernel<true><<<nblocks, kBucketThreads, 0, sb>>>(ap, cn, m, pp.ctl, pp.list, list_stride);
-            else bucket_kernel<false><<<nblocks, kBucketThreads, 0, sb>>>(ap, cn, m, pp.ctl, pp.list, list_stride);
+            ScopedKernelTimer timer(kKindTile, st);
+            if (nvec) tile_kernel<true><<<nvec, kTileThreads, 0, st>>>(ap, cn, m, pp.ctl, pp.el, 0, nblocks);
+            if (nblocks > nvec)
+                tile_kernel<false><<<nblocks - nvec, kTileThreads, 0, st>>>(ap, cn, m, pp.ctl, pp.el, nvec, nblocks);
         }
-        count_launch(1);
+        count_launch((nvec ? 1 : 0) + (nblocks > nvec ? 1 : 0));
     };
-    // method kernels of one pass, on the caller's stream.  Counts and list bases stay on the
-    // device: the kernels read them there, so the host never waits for the histogram (empty
-    // buckets cost one near-empty launch).
-    // The buckets of a pass are independent (disjoint elements, disjoint record regions), so the
-    // small ones run on two helper streams beside the big ones: their kernels, which are mostly
-    // launch tail, fill the tails of the others.  s1/s2 == s serialises everything on `s`.
-    auto sampling = [&](const FillArgs& ap, uint32_t cn, const Prep& pp, cudaStream_t s1, cudaStream_t s2) {
+    // The divergent buckets of one pass.  Counts and record bases stay on the device: the kernels read
+    // them there, so the host never waits for the histogram (an empty bucket costs one near-empty launch).
+    // The buckets are independent (disjoint elements, disjoint record regions): s1 == s2 serialises them.
+    auto bucket_pass = [&](const FillArgs& ap, uint32_t cn, const Prep& pp, cudaStream_t s1, cudaStream_t s2) {
         uint32_t* ctl = pp.ctl;
-        auto bucket = [&](int q) { return Bucket{pp.list, ctl, q, 0, list_stride, params, 0}; };
+        auto bucket = [&](int q) {
+            const size_t o = (size_t)list_slot(q) * pp.el.stride;
+            return Bucket{pp.el.idx + o, pp.el.h + o, pp.el.z + o, ctl, q, 0, params, 0};
+        };
         if (m == kHybrid || m == kSaddle) {
-            launch_method<SaddleFar, kFuseFar>(d, 4, ap, bucket(kBSaddleFar), cn, ctl + kCtlWork + kBSaddleFar, s);
-            launch_method<SaddleFar, kFuseMid>(d, 6, ap, bucket(kBSaddleMid), cn, ctl + kCtlWork + kBSaddleMid, s1);
             launch_method<SaddleLeft, kFuseLeft>(d, 3, ap, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s1);
+            launch_method<SaddleFar, kFuseMid>(d, 6, ap, bucket(kBSaddleMid), cn, ctl + kCtlWork + kBSaddleMid, s2);
             launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s2);
         }
         if (m == kHybrid || m == kAlternate) {
-            launch_method<Alternate>(d, 1, ap, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s2);
-            launch_method<AlternateLeft, kFuseAltLeft>(d, 5, ap, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft,
-                                         m == kAlternate ? s : s1);
+            launch_method<Alternate>(d, 1, ap, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s1);
+            launch_method<AlternateLeft, kFuseAltLeft>(d, 5, ap, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft, s2);
         }
-        if (m == kHybrid || m == kDevroye) {
-            launch_method<DevroyeT<kDevroyePair>, kFuseDevroye>(d, 0, ap, bucket(kBDevroye), cn, ctl + kCtlWork + kBDevroye, s2);
-            launch_method<DevroyeT<kDevroyeMSH>, kFuseDevroye>(d, 0, ap, bucket(kBDevroyeMSH), cn, ctl + kCtlWork + kBDevroyeMSH,
-                                                 m == kDevroye ? s : s1);
-        }
-        if (m == kHybrid) launch_dense<kNormal>(d, ap, bucket(kBNormal), cn, s);
     };
+    const bool any_buckets = (m != kDevroye);  // explicit devroye is drawn entirely inside the tiles
 
-    const bool multi = cmax_elems >= multi_min() && getenv("PGM_CUDA_NO_OVERLAP") == nullptr;
-    if (!overlap && !multi) {
+    const bool multi = !no_overlap && any_buckets && (nprep == 2 || cmax_elems >= multi_min());
+    if (!multi) {
         for (uint64_t off = 0; off < n; off += chunk) {
             const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
             a.base = base0 + off;
-            bucketing(a, cn, prep[0], s);
-            sampling(a, cn, prep[0], s, s);
+            tile_pass(a, cn, prep[0], s);
+            if (any_buckets) bucket_pass(a, cn, prep[0], s, s);
         }
         cudaFreeAsync(ws, s);
         return (int)cudaGetLastError();
     }
 
     // (the caller's stream `s` may be the null handle of the default stream: compare helpers only)
-    cudaStream_t hb = overlap ? helper_stream(0) : nullptr;
-    cudaStream_t h1 = multi ? helper_stream(1) : nullptr, h2 = multi ? helper_stream(2) : nullptr;
-    if ((overlap && hb == nullptr) || (multi && (h1 == nullptr || h2 == nullptr))) {
+    cudaStream_t h1 = helper_stream(0), h2 = helper_stream(1);
+    if (h1 == nullptr || h2 == nullptr) {
         cudaFreeAsync(ws, s);
         return (int)cudaErrorUnknown;
     }
-    cudaStream_t sb = overlap ? hb : s;
-    cudaStream_t s1 = multi ? h1 : s, s2 = multi ? h2 : s;
-    // 0 ready, 1-2 prep[buf], 3-4 used[buf], 5 go, 6-7 helper streams done.  One set per host thread
-    // and device, created once: a wait captures the record that precedes it, so re-recording an event
-    // in the next call cannot disturb the waits of this one, and no other thread touches the set.
+    // 0-1 tile[buf], 2-3 helper 1 done with pass of parity buf, 4-5 helper 2 likewise.  One set per host
+    // thread and device, created once: a wait captures the record that precedes it, so re-recording an
+    // event in the next call cannot disturb the waits of this one, and no other thread touches the set.
     struct EventSet {
-        cudaEvent_t ev[8];
+        cudaEvent_t ev[6];
         bool ready = false;
     };
     static thread_local EventSet t_events[64];
@@ -1048,38 +1264,33 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         }
         es.ready = true;
     }
-    cudaEvent_t* ev = es.ev;
-    cudaEvent_t ev_ready = ev[0], *ev_prep = ev + 1, *ev_used = ev + 3, ev_go = ev[5], *ev_done = ev + 6;
-    cudaEventRecord(ev_ready, s);  // inputs and the scratch allocation are ordered before this point
-    if (overlap) cudaStreamWaitEvent(sb, ev_ready, 0);
+    cudaEvent_t *ev_tile = es.ev, *ev_d1 = es.ev + 2, *ev_d2 = es.ev + 4;
     uint64_t k = 0;
     for (uint64_t off = 0; off < n; off += chunk, ++k) {
-        const int buf = overlap ? (int)(k & 1) : 0;
+        const int buf = (int)(k & 1);
         const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
         a.base = base0 + off;
-        if (overlap) {
-            if (k >= 2) cudaStreamWaitEvent(sb, ev_used[buf], 0);  // pass k-2 is done with this scratch set
-            bucketing(a, cn, prep[buf], sb);
-            cudaEventRecord(ev_prep[buf], sb);
-            cudaStreamWaitEvent(s, ev_prep[buf], 0);
+        if (k >= 2) {  // pass k-2's bucket kernels are done with this set of lists
+            cudaStreamWaitEvent(s, ev_d1[buf], 0);
+            cudaStreamWaitEvent(s, ev_d2[buf], 0);
         }
-        else {
-            bucketing(a, cn, prep[buf], s);
+        tile_pass(a, cn, prep[buf], s);
+        cudaEventRecord(ev_tile[buf], s);
+        cudaStreamWaitEvent(h1, ev_tile[buf], 0);
+        cudaStreamWaitEvent(h2, ev_tile[buf], 0);
+        if (k >= 1) {  // the record region is shared: all of pass k-1's bucket kernels first
+            cudaStreamWaitEvent(h1, ev_d2[buf ^ 1], 0);
+            cudaStreamWaitEvent(h2, ev_d1[buf ^ 1], 0);
         }
-        if (multi) {
-            // `s` is past the previous pass (it joined the helpers there) and past this pass's bucketing
-            cudaEventRecord(ev_go, s);
-            cudaStreamWaitEvent(s1, ev_go, 0);
-            cudaStreamWaitEvent(s2, ev_go, 0);
-        }
-        sampling(a, cn, prep[buf], s1, s2);
-        if (multi) {
-            cudaEventRecord(ev_done[0], s1);
-            cudaEventRecord(ev_done[1], s2);
-            cudaStreamWaitEvent(s, ev_done[0], 0);
-            cudaStreamWaitEvent(s, ev_done[1], 0);
-        }
-        if (overlap) cudaEventRecord(ev_used[buf], s);
+        bucket_pass(a, cn, prep[buf], h1, h2);
+        cudaEventRecord(ev_d1[buf], h1);
+        cudaEventRecord(ev_d2[buf], h2);
+    }
+    // join: the last two passes' bucket kernels (earlier ones precede them in stream order)
+    for (int b2 = 0; b2 < (k >= 2 ? 2 : 1); ++b2) {
+        const int buf = (int)((k - 1 - b2) & 1);
+        cudaStreamWaitEvent(s, ev_d1[buf], 0);
+        cudaStreamWaitEvent(s, ev_d2[buf], 0);
     }
     cudaFreeAsync(ws, s);
     return (int)cudaGetLastError();
@@ -1114,7 +1325,7 @@ measure_fp64_peak(double* tflops, cudaStream_t s)
     DeviceInfo d = device_info();
     double* sink = nullptr;
     cudaError_t e;
-    if ((e = cudaMallocAsync(&sink, sizeof(double), s)) != cudaSuccess) return (int)e;
+    if ((e = (cudaError_t)scratch_alloc((void**)&sink, sizeof(double), s)) != cudaSuccess) return (int)e;
     const int iters = 4096, blocks = d.sms * 8;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
