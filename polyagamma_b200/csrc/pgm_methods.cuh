@@ -32,7 +32,7 @@ using fm::exp;
 using fm::log;
 using fm::sqrt;
 
-constexpr int kMaxRecordFields = 9;  // saddle-full is the largest record
+constexpr int kMaxRecordFields = 8;  // saddle-full is the largest record
 
 // Which sampling kernels keep a single out-of-line copy of the Philox block function (bit i =
 // method i in launch order: 0 devroye, 1 alternate, 2 saddle-full, 3 saddle-left, 4 saddle-far,
@@ -680,15 +680,14 @@ solve(double x, double u, double& f, double& fp)
     return u;
 }
 
-// Starting points for the two per-(h, z) solves of the setup, K'(u) = 2.75 xl and K'(u) = 3 xl with
+// Starting points for the two per-(h, z) solves of the FULL setup, K'(u) = 2.75 xl and K'(u) = 3 xl with
 // xl = tanh(zz)/zz: both are functions of zz alone, tabulated on zz in [0, kGuessZMax] (step
-// 1/16, filled once per device by init_guess_tables_kernel with the solver itself) and
+// 1/16, filled once per device by init_tables_kernel with the solver itself) and
 // interpolated linearly -- error ~1e-4, so one Halley step lands below the 1e-9 tolerance and
 // every lane of a warp takes the same two evaluations.
 constexpr double kGuessZMax = 26.0;
 constexpr int kGuessPerUnit = 16;
 constexpr int kGuessN = (int)(kGuessZMax * kGuessPerUnit) + 2;
-static __device__ double g_guess_uc[kGuessN];
 static __device__ double g_guess_ur[kGuessN];
 
 __device__ __forceinline__ double
@@ -699,6 +698,73 @@ table_interp(const double* tab, double zz)
     double fr = pos - i;
     double a = __ldg(tab + i), b = __ldg(tab + i + 1);
     return a + (b - a) * fr;
+}
+
+// ---- the saddle point as a table ---------------------------------------------------------------------
+// K'(u) = x defines ONE function u(x), whatever h and z are (the reference solves it by Newton-Raphson for
+// every proposal, src/pgm_saddle.c:140-158,235-244).  The acceptance test needs two functions of it,
+//     G(x) = K0(u(x)) - u(x) x      (K0 = cumulant without its log cosh z offset; dG/dx = -u)
+//     D(x) = K2(u(x))               (K2 = second derivative of the cumulant),
+// and only through the combinations
+//     Gr(x) = G(x) + 1/(2x) - log 2,      Hr(x) = 1/2 log(D(x) / x^3),
+// which are smooth, bounded, and vanish like e^{-2/x} as x -> 0 (G ~ -1/(2x) + log 2, D ~ x^3 there).  Both
+// are tabulated per device as cubic Hermite pieces on a grid that follows the floating-point format --
+// 2^kTabBits cells per binade of x, so the cell index is a shift of the high word -- over x in
+// [2^kTabEmin, 2^kTabEmax).  Interpolation error < 4e-11 absolute (tests/test_gpu_parity.py::
+// test_saddle_table against the direct solve); below the range both functions are < 1e-25 (taken as 0),
+// above it (x >= 8: a right-piece proposal far in the tail) the direct solve runs.
+// Every lane of a warp therefore takes the same dozen instructions per proposal instead of one to four
+// tanh / tan evaluations: the far / mid / left split of the saddle buckets (round 1) is gone.
+constexpr int kTabBits = 7;
+constexpr int kTabEmin = -5, kTabEmax = 3;
+constexpr int kTabCells = (kTabEmax - kTabEmin) << kTabBits;
+static __device__ double2 g_saddle_tab[4 * kTabCells];  // per cell: cubic in t of Gr (c0 c1 | c2 c3), then of Hr
+
+// Gr, Hr and their x-derivatives by the direct solve (table generation; x outside the table)
+static __device__ __noinline__ void
+eval_direct(double x, double& gr, double& dgr, double& hr, double& dhr)
+{
+    double u = table_guess(x), f = 0.0, fp = 1.0, fpp = 0.0;
+    for (int n = 0; n < 80; ++n) {  // Halley, to the last bit
+        kprime3(u, f, fp, fpp);
+        const double g = f - x;
+        const double den = 2.0 * fp * fp - g * fpp;
+        const double du = (den > 0.0) ? 2.0 * g * fp / den : g / fp;
+        double un = u - du;
+        if (un >= kUMax) un = 0.5 * (u + kUMax);
+        const bool done = (un == u) || fabs(du) <= 2e-16 * fabs(u);
+        u = un;
+        if (done) break;
+    }
+    kprime3(u, f, fp, fpp);
+    const double rx = 1.0 / x;
+    gr = (cumulant0(u, f) - u * x) + 0.5 * rx - kLog2;
+    dgr = -u - 0.5 * rx * rx;
+    hr = 0.5 * ::log(fp * rx * rx * rx);
+    dhr = 0.5 * (fpp / (fp * fp) - 3.0 * rx);  // dD/dx = K3 du/dx = K3 / K2
+}
+
+__device__ __forceinline__ void
+lookup(double x, double& gr, double& hr)
+{
+    const int hi = __double2hiint(x);
+    const int cell = (hi >> (20 - kTabBits)) - ((1023 + kTabEmin) << kTabBits);
+    if ((unsigned)cell >= (unsigned)kTabCells) {
+        gr = 0.0;
+        hr = 0.0;
+        if (cell > 0) {
+            double d0, d1;
+            eval_direct(x, gr, d0, hr, d1);
+        }
+        return;
+    }
+    const double x0 = __hiloint2double(hi & ~((1 << (20 - kTabBits)) - 1), 0);                // left end of the cell
+    const double inv_w = __hiloint2double(((2046 + kTabBits) << 20) - (hi & 0x7ff00000), 0);  // 1 / cell width
+    const double t = (x - x0) * inv_w;
+    const double2* c = g_saddle_tab + 4 * cell;
+    const double2 g01 = __ldg(c), g23 = __ldg(c + 1), h01 = __ldg(c + 2), h23 = __ldg(c + 3);
+    gr = fma(fma(fma(g23.y, t, g23.x), t, g01.y), t, g01.x);
+    hr = fma(fma(fma(h23.y, t, h23.x), t, h01.y), t, h01.x);
 }
 
 // invgauss_logcdf (src/pgm_saddle.c:282-292)
@@ -721,112 +787,99 @@ invgauss_logcdf(double x, double mu, double lambda)
 }  // namespace saddle
 
 // Elements of the saddle method whose right envelope piece is unreachable (weight < 2^-33, see
-// tools/saddle_right_weight.py for the map of log10 w_right over (h, |z|/2)).  Only used with
+// tools/saddle_right_weight.py for the map of log10 w_right over (h, |z|/2)): the 32-bit mixture uniform can
+// never select it, so neither the right tangent nor the incomplete gamma function is needed.  Only used with
 // the consistent envelope; ref_compat keeps the reference's (much larger) right weight.
-// A further split keeps warps homogeneous: for |z| >= 8 (zz >= 4) the proposals sit around
-// xl = tanh(zz)/zz <= 1/4, where the large-argument starting point solves K'(u) = x in one or two
-// evaluations, and u < 0 always (x < xc < 1: tanh branch only); for smaller |z| the solve starts
-// from the Taylor expansion and takes two or three.  Mixing both in a warp left half of its lanes
-// idle (ncu: 17 of 32 lanes active).
-enum : int { kSaddleFar = 0, kSaddleLeft = 1, kSaddleFull = 2 };
+enum : int { kSaddleLeft = 1, kSaddleFull = 2 };
 
 __host__ __device__ __forceinline__ int
 saddle_mode(double h, double z, bool compat)
 {
-    if (compat || !(h * (1.0 + 0.125 * fabs(z)) >= 22.0)) return kSaddleFull;
-    return fabs(z) >= 8.0 ? kSaddleFar : kSaddleLeft;
+    return (compat || !(h * (1.0 + 0.125 * fabs(z)) >= 22.0)) ? kSaddleFull : kSaddleLeft;
 }
 
 template <int MODE>
 struct SaddleT {
-    using Rng = RngFor<(MODE == kSaddleFull ? 2 : MODE == kSaddleLeft ? 3 : 4)>;
+    using Rng = RngFor<(MODE == kSaddleFull ? 2 : 3)>;
     static constexpr bool FULL = (MODE == kSaddleFull);
-    static constexpr bool FAR = (MODE == kSaddleFar);
-    // h, zz, xl, c_l [, a1, a2 [, w_left, c_r, slope_r]]  (the far kernel never uses the expansion)
-    static constexpr int kFields = FULL ? 9 : FAR ? 4 : 6;
+    // h, xl, kappa, A [, w_left, kappa_r, A_r, slope_r]
+    static constexpr int kFields = FULL ? 8 : 4;
 
     struct Par {
-        double h, inv_h, half_z2, xl, xc, slope_l, c_l, a1, a2;
-        double w_left, c_r, slope_r;  // FULL only
+        double h, inv_h, xl, xc, kappa, A;
+        double w_left, kappa_r, A_r, slope_r;  // FULL only
     };
     struct State {
         double acc;
     };
 
-    // set_sampling_parameters (src/pgm_saddle.c:180-230) + mixture weight (:317-328, log space)
+    // set_sampling_parameters (src/pgm_saddle.c:180-230) + mixture weight (:317-328, log space).
+    // With L_l(x) = slope_l x + icpt_l the left tangent (slope_l = -1/(2 xl^2), icpt_l = 1/xl - 1/(2 xc)) and
+    // alpha_l = K2(u(xc)) / xc^3, the left acceptance test  U k_l(x) <= phi(x)  (bounding_kernel :250-263,
+    // saddle_point :235-244, common sqrt(h / 2 pi) cancelled) reads, in the tabulated functions,
+    //     log U + Hr(x) <= h (Gr(x) - kappa x) + A,
+    //     kappa = z^2/2 + slope_l,   A = h (log 2 + log cosh z - 1/xl) + Hr(xc)      (z halved)
+    // -- the 1/(2x) of the envelope cancels the one in G.
     static __device__ inline void make_record(double h, double z, bool compat, double* rec)
     {
         using namespace saddle;
         double zz = 0.5 * fabs(z);
         if (!(zz > 0.0)) zz = 0.0;
-        double xl, half_z2, log_cosh_z;
+        double xl, half_z2, l2cz;  // l2cz = log 2 + log cosh(zz) = zz + log1p(e^{-2 zz})
         // (below 1e-100 every quantity here equals its z = 0 value in double precision; the cut keeps
         // the MUFU-seeded reciprocals on normal numbers)
         if (zz > 1e-100) {
             const double e = exp(-2.0 * zz);
             xl = fm::div(1.0 - e, (1.0 + e) * zz);  // tanh(zz) / zz
             half_z2 = 0.5 * zz * zz;
-            // log cosh(zz) = zz - log 2 + log1p(e^{-2 zz})
-            log_cosh_z = zz - kLog2 + (e < 2.5e-3 ? e * (1.0 - e * (0.5 - e * (1.0 / 3.0 - 0.25 * e))) : log1p(e));
+            l2cz = zz + log(1.0 + e);  // (absolute accuracy is what counts here: no log1p needed)
         }
         else {
             xl = 1.0;
             half_z2 = 0.0;
-            log_cosh_z = 0.0;
+            l2cz = kLog2;
         }
         const double xc = 2.75 * xl;
-        const double xc_inv = fm::rcp(xc);
-        const double xl_inv = 2.75 * xc_inv;
-        double f, fp_c;
-        const bool tabulated = zz < kGuessZMax;
-        (void)solve<FAR>(xc, tabulated ? table_interp(g_guess_uc, zz) : table_guess(xc), f, fp_c);
-        const double alpha_r = fp_c * xc_inv * xc_inv;  // K2(u(xc)) / xc^2, K2 = second derivative
-        const double alpha_l = xc_inv * alpha_r;
-        const double icpt_l = -0.5 * xc_inv + xl_inv;  // cumulant(ul) = 0, src/pgm_saddle.c:216
+        const double xl_inv = fm::rcp(xl);
+        double gr_c, hr_c;
+        lookup(xc, gr_c, hr_c);
+        const double slope_l = -0.5 * xl_inv * xl_inv;
         rec[0] = h;
-        rec[1] = zz;
-        rec[2] = xl;
-        // constant part of  log k_l(x) - log phi(x)  (bounding_kernel :250-263, saddle_point :235-244)
-        rec[3] = 0.5 * h * xc_inv + h * icpt_l - 0.5 * log(alpha_l) - h * log_cosh_z;
-        if (!FAR) {
-            // second-order expansion of u(x) about x = xl, where u = -zz^2/2 and K1(u) = xl exactly:
-            // du/dx = 1 / K2, d2u/dx2 = -K3 / K2^3  (K1, K2, K3 = derivatives of the cumulant)
-            double fp_l, fpp_l;
-            if (zz * zz < 1e-4) {
-                double f_l;
-                kprime3(-half_z2, f_l, fp_l, fpp_l);
-            }
-            else {
-                const double inv = -fm::rcp(zz * zz);
-                const double t = (1.0 - xl) * inv;
-                fp_l = xl * xl + t;
-                fpp_l = 2.0 * xl * fp_l - fp_l * inv - 2.0 * t * inv;
-            }
-            const double a1 = fm::rcp(fp_l);
-            rec[4] = a1;
-            rec[5] = -0.5 * fpp_l * a1 * a1 * a1;
-        }
+        rec[1] = xl;
+        rec[2] = half_z2 + slope_l;
+        rec[3] = h * (l2cz - xl_inv) + hr_c;
         if (FULL) {
+            const double log_cosh_z = l2cz - kLog2;
+            const double xc_inv = fm::rcp(xc);
+            const double icpt_l = -0.5 * xc_inv + xl_inv;  // cumulant(ul) = 0, src/pgm_saddle.c:216
             const double logxl = log(xl);
             const double xr = 3.0 * xl;
-            double fp_r;
+            double f, fp_r;
+            const bool tabulated = zz < kGuessZMax;
             double ur = solve(xr, tabulated ? table_interp(g_guess_ur, zz) : table_guess(xr), f, fp_r);
             const double tr = ur + half_z2;
             const double logxc = 1.0116009116784799 + logxl;  // log(2.75)
             const double slope_r = -tr - fm::rcp(xr);
             const double icpt_r = (log_cosh_z + cumulant0(ur, f)) + 1.0 - 1.0986122886681098 - logxl + logxc;
             const double log_sqrt_h2pi = 0.5 * log(h / (2.0 * kPi));
-            const double log_coef_r = log_sqrt_h2pi - 0.5 * log(alpha_r);
-            double lp = h * (0.5 * xc_inv + icpt_l - xl_inv) + invgauss_logcdf(xc, xl, h) - 0.5 * log(alpha_l);
+            // 1/2 log alpha_l = Hr(xc);  1/2 log alpha_r = Hr(xc) + 1/2 log xc   (alpha_r = K2(u(xc)) / xc^2)
+            const double half_log_alpha_r = hr_c + 0.5 * logxc;
+            const double log_coef_r = log_sqrt_h2pi - half_log_alpha_r;
+            double lp = h * (0.5 * xc_inv + icpt_l - xl_inv) + invgauss_logcdf(xc, xl, h) - hr_c;
             const double hrho = -h * slope_r;
             double lq = log_upper_gamma(h, hrho * xc, false) + log_coef_r +
                         h * (icpt_r - (compat ? 0.0 : logxc) - log(hrho));
             double w_left = 1.0 / (1.0 + exp(lq - lp));
             if (!(w_left >= 0.0)) w_left = 1.0;
-            rec[6] = w_left;
-            // src/pgm_saddle.c:257 uses +log(xc); the derivation needs -log(xc) (SURVEY 8-DEFECTS i)
-            rec[7] = h * ((compat ? logxc : -logxc) + icpt_r) - 0.5 * log(alpha_r) - h * log_cosh_z;
-            rec[8] = slope_r;
+            rec[4] = w_left;
+            // right test:  log U + log k_r(x) <= log phi(x)  with  log k_r = h slope_r x + (h - 1) log x + c_r,
+            // c_r = h (-+log xc + icpt_r) - 1/2 log alpha_r - h log cosh z  (src/pgm_saddle.c:257 uses +log(xc);
+            // the derivation needs -log(xc), SURVEY 8-DEFECTS i); in the tabulated functions
+            //     log U + Hr(x) + (h + 1/2) log x + h kappa_r x + h / (2x) <= h Gr(x) + A_r
+            const double c_r = h * ((compat ? logxc : -logxc) + icpt_r) - half_log_alpha_r - h * log_cosh_z;
+            rec[5] = slope_r + half_z2;
+            rec[6] = h * kLog2 - c_r;
+            rec[7] = slope_r;
         }
     }
 
@@ -835,27 +888,21 @@ struct SaddleT {
     {
         p.h = rec[0];
         p.inv_h = fm::rcp(p.h);
-        double zz = rec[1];
-        p.half_z2 = 0.5 * zz * zz;
-        p.xl = rec[2];
+        p.xl = rec[1];
         p.xc = 2.75 * p.xl;
-        p.slope_l = -0.5 * fm::rcp(p.xl * p.xl);
-        p.c_l = rec[3];
-        if (!FAR) {
-            p.a1 = rec[4];
-            p.a2 = rec[5];
-        }
+        p.kappa = rec[2];
+        p.A = rec[3];
         if (FULL) {
-            p.w_left = rec[6];
-            p.c_r = rec[7];
-            p.slope_r = rec[8];
+            p.w_left = rec[4];
+            p.kappa_r = rec[5];
+            p.A_r = rec[6];
+            p.slope_r = rec[7];
         }
         s.acc = 0.0;
         return true;
     }
 
     // One pass of the proposal loop of random_polyagamma_saddle (src/pgm_saddle.c:331-347).
-    // Accept iff  log U + log k(x) <= log phi(x); the common sqrt(h / 2 pi) has been cancelled.
     static __device__ __forceinline__ bool step(Par& p, State& s, Rng& r, bool)
     {
         using namespace saddle;
@@ -866,9 +913,11 @@ struct SaddleT {
         if (FULL) left = um < p.w_left;
         if (left) {
             const double mu = p.xl, mu2 = p.xl * p.xl;
-            do {  // IG(mu = xl, lambda = h) | x < xc, Michael-Schucany-Haas
-                double y = r.normal();
-                double w = mu + 0.5 * mu2 * y * y * p.inv_h;
+            do {  // IG(mu = xl, lambda = h) | x < xc, Michael-Schucany-Haas; only the normal's square is needed
+                const double L = -log(r.uniform_oc());
+                const double c = fm::cos2pi(r.uniform_co());
+                const double y2 = 2.0 * L * c * c;
+                double w = mu + 0.5 * mu2 * y2 * p.inv_h;
                 x = mu2 * fm::rcp(w + sqrt(fmax(w * w - mu2, 0.0)));
                 if (r.uniform_co() * (mu + x) > mu) {
                     x = mu2 * fm::rcp(x);
@@ -878,54 +927,15 @@ struct SaddleT {
         else {
             x = left_bounded_gamma(r, h, -h * p.slope_r, p.xc);
         }
-        // Acceptance: log U + log k(x) <= log phi(x) with (saddle_point :235-244, bounding_kernel
-        // :250-263, common sqrt(h / 2 pi) cancelled)
-        //   log phi = h (K(u) - t x) - 1/2 log K''(u),  t = u + z^2/2,  K'(u) = x
-        //   log k_l = h (slope_l x - 1/(2x)) - 3/2 log x + c_l          (x <= xc)
-        //   log k_r = h slope_r x + (h - 1) log x + c_r                 (x >  xc)
-        const double rx = fm::rcp(x);
-        double u, fp, cum;
-        if (x <= 0.2) {
-            // large-argument closed form: tanh(s)/s = x solved to < 1e-10 relative by the two-pass
-            // fixed point behind asymptotic_guess, so K' = x, K'' = x^2 + (1 - x)/(2u) and
-            // -log cosh s = -(s - log 2 + log1p(e^{-2s})) need no further evaluation of tanh
-            const double e = exp(-2.0 * rx);
-            const double corr = 2.0 * e - e * e * (2.0 - 8.0 * rx);
-            const double sx = (1.0 - corr) * rx;         // s = sqrt(-2u)
-            const double dl = 2.0 * corr * rx;            // 2 (1/x - s)
-            const double e2s = e * (1.0 + dl * (1.0 + 0.5 * dl));  // e^{-2s}
-            const double inv_s2 = fm::rcp(sx * sx);
-            u = -0.5 * sx * sx;
-            fp = x * x - (1.0 - x) * inv_s2;
-            cum = -(sx - kLog2 + e2s * (1.0 - e2s * (0.5 - e2s * (1.0 / 3.0))));
-        }
-        else {
-            double u0;
-            const double d = x - p.xl;
-            if (x <= 0.25) {
-                u0 = asymptotic_guess(x);
-            }
-            else if (!FAR && fabs(d) <= 0.5 * p.xl) {
-                u0 = fmin(-p.half_z2 + d * (p.a1 + p.a2 * d), kUMax - 1e-3);
-            }
-            else {
-                u0 = table_guess(x);
-            }
-            double f;
-            u = solve<FAR>(x, u0, f, fp);
-            cum = cumulant0(u, f);
-        }
-        const double t = u + p.half_z2;
-        const double um2 = r.uniform32();
+        double gr, hr;
+        lookup(x, gr, hr);
+        const double lu = log(r.uniform32());
         bool accept;
         if (FULL && x > p.xc) {
-            const double lk = h * p.slope_r * x + (h - 1.0) * log(x) + p.c_r;
-            accept = log(um2) + lk <= h * (cum - t * x) - 0.5 * log(fp);
+            accept = lu + hr + (h + 0.5) * log(x) + h * (p.kappa_r * x + 0.5 * fm::rcp(x)) <= h * gr + p.A_r;
         }
         else {
-            // the three logarithms (U, x^-3/2, K''^1/2) folded into one
-            const double lhs = 0.5 * log(um2 * um2 * fp * rx * rx * rx);
-            accept = lhs <= h * (cum - t * x) - h * (p.slope_l * x - 0.5 * rx) - p.c_l;
+            accept = lu + hr <= h * (gr - p.kappa * x) + p.A;
         }
         if (accept) {
             s.acc = 0.25 * h * x;
@@ -937,7 +947,6 @@ struct SaddleT {
 
 using SaddleFull = SaddleT<kSaddleFull>;
 using SaddleLeft = SaddleT<kSaddleLeft>;
-using SaddleFar = SaddleT<kSaddleFar>;
 
 
 // =========================================================================================

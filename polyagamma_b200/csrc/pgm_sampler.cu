@@ -141,8 +141,8 @@ invalid_h(double h, double& value)
 // buckets
 // ---------------------------------------------------------------------------------------
 // bucket ids (the gamma method never needs the tile pass: it runs on the identity range)
-enum : int { kBDevroye = 0, kBAlternate = 1, kBSaddleFull = 2, kBSaddleLeft = 3, kBSaddleFar = 4, kBAlternateLeft = 5,
-             kBSaddleMid = 6, kBNormal = 7, kBDevroyeMSH = 8, kNumBuckets = 9, kBGamma = 9 };
+enum : int { kBDevroye = 0, kBAlternate = 1, kBSaddleFull = 2, kBSaddleLeft = 3, kBAlternateLeft = 4, kBNormal = 5,
+             kBDevroyeMSH = 6, kNumBuckets = 7, kBGamma = 7 };
 constexpr uint32_t kBucketNone = 15;
 
 // ctl layout (uint32): [0..9] bucket counts, [10..19] record bases, [20..29] work counters, [30] ticket
@@ -158,17 +158,32 @@ bucket_of(int method, double h, double z, bool compat)
     // |z|/2 < 1/T: exponential-pair proposal, else Michael-Schucany-Haas
     const int bd = (0.5 * az >= 1.5625) ? kBDevroyeMSH : kBDevroye;
     const int ba = alternate_left_only(z) ? kBAlternateLeft : kBAlternate;
-    // the far kernel's buckets: |z| >= 14 (proposals below x = 0.2 almost surely: closed-form solve for every
-    // lane) and 8 <= |z| < 14 (a mix of closed-form and iterative solves)
-    const int sm = saddle_mode(h, z, compat);
-    const int bs = sm == kSaddleFull ? kBSaddleFull : sm == kSaddleLeft ? kBSaddleLeft
-                   : az >= 14.0 ? kBSaddleFar : kBSaddleMid;
+    const int bs = saddle_mode(h, z, compat) == kSaddleFull ? kBSaddleFull : kBSaddleLeft;
     return method == kNormal ? kBNormal : method == kSaddle ? bs : method == kDevroye ? bd
            : method == kAlternate ? ba : kBGamma;
 }
 
+// bucket_of(hybrid_select(h, z) or the explicit method, h, z) for the tile kernel, which classifies eight elements
+// per thread: every predicate is evaluated, nothing branches (the switch / early-return forms above compile
+// to a jump table and a dozen divergent branches per element).  `method` is warp-uniform.
+__device__ __forceinline__ uint32_t
+classify(int method, double h, double z, bool compat)
+{
+    const double az = fabs(z);  // (z = NaN fails every test: it is sampled as z = 0)
+    const bool p_norm = h > 50.0;
+    const bool p_sad = (h >= 8.0) | ((h > 4.0) & (z <= 4.0));
+    const bool p_dev = (h == 1.0) | ((h == floor(h)) & (z <= 1.0));
+    const bool p_full = compat | !(h * fma(0.125, az, 1.0) >= 22.0);
+    const uint32_t bs = p_full ? (uint32_t)kBSaddleFull : (uint32_t)kBSaddleLeft;
+    const uint32_t ba = (az >= 14.0) ? (uint32_t)kBAlternateLeft : (uint32_t)kBAlternate;
+    const uint32_t bd = (az >= 3.125) ? (uint32_t)kBDevroyeMSH : (uint32_t)kBDevroye;
+    const uint32_t hyb = p_norm ? (uint32_t)kBNormal : p_sad ? bs : p_dev ? bd : ba;
+    const uint32_t expl = (method == kSaddle) ? bs : (method == kDevroye) ? bd : ba;
+    return (method == kHybrid) ? hyb : expl;
+}
+
 // Where a bucket's elements are drawn.  The near-dense, short-setup buckets (normal approximation,
-// far saddle, both devroye proposals: 91 % of cfg4, all of cfg2) are drawn INSIDE tile_kernel, from
+// left-only saddle, both devroye proposals: 96 % of cfg4, all of cfg2) are drawn INSIDE tile_kernel, from
 // shared memory, and their outputs leave the SM as part of the tile's coalesced store.  The divergent
 // buckets go to global element lists: slot s of the pass's ElemLists holds (index, h, z) of its
 // elements, compacted, so the per-method kernels read contiguously instead of gathering 8-byte
@@ -179,13 +194,11 @@ list_slot(int bucket)
     switch (bucket) {
         case kBAlternate: return 0;
         case kBSaddleFull: return 1;
-        case kBSaddleLeft: return 2;
-        case kBAlternateLeft: return 3;
-        case kBSaddleMid: return 4;
+        case kBAlternateLeft: return 2;
         default: return -1;  // drawn in the tile
     }
 }
-constexpr int kNumListSlots = 5;
+constexpr int kNumListSlots = 3;
 
 struct ElemLists {
     uint32_t* idx;  // slot s: idx + s * stride, h + s * stride, z + s * stride
@@ -283,37 +296,13 @@ struct LocalRec {
 constexpr int kTileThreads = 256;
 constexpr int kTileItems = 8;
 constexpr int kTile = kTileThreads * kTileItems;
+#ifndef PGM_TILE_WARP_SHARE
+#define PGM_TILE_WARP_SHARE 128
+#endif
+constexpr uint32_t kTileWarpShare = PGM_TILE_WARP_SHARE;  // list entries per participating warp
 #ifndef PGM_TILE_BLOCKS_PER_SM
 #define PGM_TILE_BLOCKS_PER_SM 4
 #endif
-
-// One batch of up to 32 far-saddle elements of a tile, drawn to completion by one warp (1.004 proposals
-// per sample: a refill loop would have nothing to refill from).
-__device__ __forceinline__ void
-tile_far_batch(const FillArgs& a, bool compat, uint64_t index0, const uint16_t* __restrict__ list, uint32_t count,
-               uint32_t first, const double* s_z, double* s_hout, uint32_t lane)
-{
-    using M = SaddleFar;
-    const uint32_t pos = first + lane;
-    bool active = pos < count;
-    M::Par par;
-    M::State st;
-    M::Rng rng;
-    uint32_t e = 0;
-    if (active) {
-        e = list[pos];
-        double loc[M::kFields];
-        M::make_record(s_hout[e], s_z[e], compat, loc);
-        M::load(LocalRec{loc}, par, st, compat);
-        rng.init(a.key, index0 + e);
-    }
-    while (__any_sync(0xffffffffu, active)) {
-        if (active && M::step(par, st, rng, compat)) {
-            s_hout[e] = st.acc;
-            active = false;
-        }
-    }
-}
 
 // persistent lanes over one in-tile list (same loop as sample_kernel, work counter in shared memory)
 template <class M>
@@ -459,11 +448,12 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
 #pragma unroll
         for (int k = 0; k < kTileItems; ++k) {
             const uint32_t e = (k >> 1) * (2 * kTileThreads) + 2 * tid + (k & 1);
-            double hk = hv[k], bad;
-            const bool inval = invalid_h(hk, bad);
-            const int m = (method == kHybrid) ? hybrid_select(hk, zv[k]) : method;
-            const uint32_t b = (e < tn && !inval) ? (uint32_t)bucket_of(m, hk, zv[k], compat) : kBucketNone;
-            hv[k] = inval ? bad : hk;  // invalid h: the output of this element
+            const double hk = hv[k];
+            // nan_or_inf (src/pgm_random.c:137-141): h <= 0 or NaN -> NaN, +inf -> +inf (h itself)
+            const bool nonpos = !(hk > 0.0);
+            const bool inval = nonpos | (hk == INFINITY);
+            const uint32_t b = (e < tn && !inval) ? classify(method, hk, zv[k], compat) : kBucketNone;
+            hv[k] = nonpos ? NAN : hk;  // invalid h: the output of this element
             const bool valid = b != kBucketNone;
             const uint32_t same = __match_any_sync(0xffffffffu, b);
             const int leader = __ffs(same) - 1;
@@ -519,43 +509,46 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
     }
 
     // ---- 4. in-tile buckets ----
-    // Far saddle and normal approximation: one work queue per tile.  Items 0 .. nfar-1 are batches of 32
-    // far-saddle elements (the expensive ones first), the rest batches of 64 normal-approximation elements
-    // (two per lane: their dependency chains interleave); a warp takes the next item when it is done with its
-    // last, so the warps of the block reach the barrier below within one item of each other.
+    // The expensive lists first (persistent lanes: a warp reserves 32 entries of the tile's list at a time
+    // and refills retired lanes from them), then the normal approximation from a work queue of batches of 64
+    // elements (two per lane: their dependency chains interleave).  Only as many warps as the list can keep
+    // full for a few trips take part in a list (a list of 400 spread over 8 warps leaves every warp with a
+    // half-empty second trip: 18 of 32 lanes); the others start on the queue at once, and a warp that finds a
+    // list exhausted moves on, so the warps of the block reach the barrier below within one item of each other.
     {
         const uint64_t index0 = a.first_index + g0;
-        const uint32_t cf = s_cnt[kBSaddleFar], cn = s_cnt[kBNormal];
-        const uint16_t* lf = s_list + s_off[kBSaddleFar];
+        const uint32_t wid = tid >> 5;
+        auto takes_part = [&](uint32_t count) { return wid * kTileWarpShare < count; };
+        if (takes_part(s_cnt[kBSaddleLeft]))
+            tile_sample<SaddleLeft>(a, compat, index0, s_list + s_off[kBSaddleLeft], s_cnt[kBSaddleLeft],
+                                    &s_next[kBSaddleLeft], s_z, s_hout, lane, lt);
+        if (takes_part(s_cnt[kBDevroye]))
+            tile_sample<DevroyeT<kDevroyePair>>(a, compat, index0, s_list + s_off[kBDevroye], s_cnt[kBDevroye],
+                                                &s_next[kBDevroye], s_z, s_hout, lane, lt);
+        if (takes_part(s_cnt[kBDevroyeMSH]))
+            tile_sample<DevroyeT<kDevroyeMSH>>(a, compat, index0, s_list + s_off[kBDevroyeMSH], s_cnt[kBDevroyeMSH],
+                                               &s_next[kBDevroyeMSH], s_z, s_hout, lane, lt);
+        const uint32_t cn = s_cnt[kBNormal];
         const uint16_t* ln = s_list + s_off[kBNormal];
-        const uint32_t nfar = (cf + 31u) >> 5, nitems = nfar + ((cn + 63u) >> 6);
+        const uint32_t nitems = (cn + 63u) >> 6;
         for (;;) {
             uint32_t it = 0;
             if (lane == 0) it = atomicAdd(&s_next[kBNormal], 1u);
             it = __shfl_sync(0xffffffffu, it, 0);
             if (it >= nitems) break;
-            if (it < nfar) {
-                tile_far_batch(a, compat, index0, lf, cf, it << 5, s_z, s_hout, lane);
-            }
-            else {
-                const uint32_t i = ((it - nfar) << 6) + lane;
-                if (i < cn) {
-                    const bool two = i + 32u < cn;
-                    const uint32_t e0 = ln[i], e1 = two ? ln[i + 32u] : e0;
-                    RngInlineRK r0, r1;
-                    r0.init(a.key, index0 + e0);
-                    r1.init(a.key, index0 + e1);
-                    const double v0 = normal_approx_sample(r0, s_hout[e0], s_z[e0]);
-                    const double v1 = normal_approx_sample(r1, s_hout[e1], s_z[e1]);
-                    if (two) s_hout[e1] = v1;
-                    s_hout[e0] = v0;
-                }
+            const uint32_t i = (it << 6) + lane;
+            if (i < cn) {
+                const bool two = i + 32u < cn;
+                const uint32_t e0 = ln[i], e1 = two ? ln[i + 32u] : e0;
+                RngInlineRK r0, r1;
+                r0.init(a.key, index0 + e0);
+                r1.init(a.key, index0 + e1);
+                const double v0 = normal_approx_sample(r0, s_hout[e0], s_z[e0]);
+                const double v1 = normal_approx_sample(r1, s_hout[e1], s_z[e1]);
+                if (two) s_hout[e1] = v1;
+                s_hout[e0] = v0;
             }
         }
-        tile_sample<DevroyeT<kDevroyePair>>(a, compat, index0, s_list + s_off[kBDevroye], s_cnt[kBDevroye],
-                                            &s_next[kBDevroye], s_z, s_hout, lane, lt);
-        tile_sample<DevroyeT<kDevroyeMSH>>(a, compat, index0, s_list + s_off[kBDevroyeMSH], s_cnt[kBDevroyeMSH],
-                                           &s_next[kBDevroyeMSH], s_z, s_hout, lane, lt);
     }
     __syncthreads();
 
@@ -793,8 +786,6 @@ small_kernel(FillArgs a, uint32_t n, int method)
             case kBAlternateLeft: v = run_one<AlternateLeft>(k0, k1, index, h, z, compat); break;
             case kBSaddleFull: v = run_one<SaddleFull>(k0, k1, index, h, z, compat); break;
             case kBSaddleLeft: v = run_one<SaddleLeft>(k0, k1, index, h, z, compat); break;
-            case kBSaddleFar:
-            case kBSaddleMid: v = run_one<SaddleFar>(k0, k1, index, h, z, compat); break;
             default: {  // kBNormal
                 RngInlineRK r;
                 r.init(a.key, a.first_index + g);
@@ -805,18 +796,34 @@ small_kernel(FillArgs a, uint32_t n, int method)
     a.out[g] = v;
 }
 
-// fills g_guess_uc / g_guess_ur (one thread per table entry)
+// fills the saddle tables (one thread per entry): the starting points of the FULL setup's right solve, and
+// the Hermite pieces of Gr and Hr (pgm_methods.cuh)
 __global__ void
-init_guess_tables_kernel()
+init_tables_kernel()
 {
     using namespace saddle;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= kGuessN) return;
-    double zz = (double)i / kGuessPerUnit;
-    double xl = zz > 0.0 ? tanh(zz) / zz : 1.0;
-    double f, fp;
-    g_guess_uc[i] = solve(2.75 * xl, table_guess(2.75 * xl), f, fp);
-    g_guess_ur[i] = solve(3.0 * xl, table_guess(3.0 * xl), f, fp);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kGuessN) {
+        double zz = (double)i / kGuessPerUnit;
+        double xl = zz > 0.0 ? tanh(zz) / zz : 1.0;
+        double f, fp;
+        g_guess_ur[i] = solve(3.0 * xl, table_guess(3.0 * xl), f, fp);
+    }
+    if (i < kTabCells) {
+        const int per = 1 << kTabBits;
+        const double w = ldexp(1.0, kTabEmin + (i >> kTabBits) - kTabBits);  // cell width
+        const double x0 = ldexp(1.0 + (double)(i & (per - 1)) / per, kTabEmin + (i >> kTabBits));
+        double g0, dg0, h0, dh0, g1, dg1, h1, dh1;
+        eval_direct(x0, g0, dg0, h0, dh0);
+        eval_direct(x0 + w, g1, dg1, h1, dh1);
+        // p(t) = f0 + m0 t + (3 df - 2 m0 - m1) t^2 + (m0 + m1 - 2 df) t^3,  m = w f'
+        const double dg = g1 - g0, dh = h1 - h0;
+        dg0 *= w, dg1 *= w, dh0 *= w, dh1 *= w;
+        g_saddle_tab[4 * i] = make_double2(g0, dg0);
+        g_saddle_tab[4 * i + 1] = make_double2(3.0 * dg - 2.0 * dg0 - dg1, dg0 + dg1 - 2.0 * dg);
+        g_saddle_tab[4 * i + 2] = make_double2(h0, dh0);
+        g_saddle_tab[4 * i + 3] = make_double2(3.0 * dh - 2.0 * dh0 - dh1, dh0 + dh1 - 2.0 * dh);
+    }
 }
 
 __global__ void
@@ -872,9 +879,9 @@ device_info()
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[1], sample_kernel<Alternate>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[2], sample_kernel<SaddleFull>, kPersistThreads, 0);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[3], sample_kernel<SaddleLeft>, kPersistThreads, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[4], sample_kernel<SaddleFar, true>, kPersistThreads, 0);
+        d.blocks_per_sm[4] = 1;  // (round 1: the far saddle kernel)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.blocks_per_sm[5], sample_kernel<AlternateLeft, true>, kPersistThreads, 0);
-        d.blocks_per_sm[6] = d.blocks_per_sm[4];
+        d.blocks_per_sm[6] = 1;  // (round 1: the far saddle kernel on 8 <= |z| < 14)
         for (int i = 0; i < 7; ++i) {
             if (d.blocks_per_sm[i] < 1) d.blocks_per_sm[i] = 1;
         }
@@ -883,7 +890,8 @@ device_info()
         cudaStream_t st = nullptr;
         cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
         if (e == cudaSuccess) {
-            init_guess_tables_kernel<<<(saddle::kGuessN + 127) / 128, 128, 0, st>>>();
+            constexpr int kEntries = saddle::kGuessN > saddle::kTabCells ? saddle::kGuessN : saddle::kTabCells;
+            init_tables_kernel<<<(kEntries + 127) / 128, 128, 0, st>>>();
             e = cudaStreamSynchronize(st);
             cudaStreamDestroy(st);
             count_launch(1);
@@ -968,7 +976,7 @@ grid_for(uint64_t full, uint64_t count_hint, uint32_t threads)
 // 1e9, setup + sampling separate -> fused): saddle-mid 2.71 -> 2.44, alternate-left 2.04 -> 1.55; saddle-left
 // gets slower (3.83 -> 4.22: its setup is longer and its lanes refill out of step), and the full saddle /
 // alternate setups are the big ones the split exists for.
-constexpr bool kFuseMid = true, kFuseLeft = false, kFuseAltLeft = true;
+constexpr bool kFuseAltLeft = true;
 
 template <class M, bool FUSED = false>
 static void
@@ -1119,9 +1127,7 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
                 case kBAlternate: launch_method<Alternate>(d, 1, a, b, cn, counters + c, s); break;
                 case kBSaddleFull: launch_method<SaddleFull>(d, 2, a, b, cn, counters + c, s); break;
                 case kBSaddleLeft: launch_method<SaddleLeft>(d, 3, a, b, cn, counters + c, s); break;
-                case kBSaddleFar: launch_method<SaddleFar>(d, 4, a, b, cn, counters + c, s); break;
                 case kBAlternateLeft: launch_method<AlternateLeft>(d, 5, a, b, cn, counters + c, s); break;
-                case kBSaddleMid: launch_method<SaddleFar>(d, 6, a, b, cn, counters + c, s); break;
                 case kBNormal: launch_dense<kNormal>(d, a, b, cn, s); break;
                 default: launch_dense<kGamma>(d, a, b, cn, s); break;
             }
@@ -1215,8 +1221,6 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
             return Bucket{pp.el.idx + o, pp.el.h + o, pp.el.z + o, ctl, q, 0, params, 0};
         };
         if (m == kHybrid || m == kSaddle) {
-            launch_method<SaddleLeft, kFuseLeft>(d, 3, ap, bucket(kBSaddleLeft), cn, ctl + kCtlWork + kBSaddleLeft, s1);
-            launch_method<SaddleFar, kFuseMid>(d, 6, ap, bucket(kBSaddleMid), cn, ctl + kCtlWork + kBSaddleMid, s2);
             launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s2);
         }
         if (m == kHybrid || m == kAlternate) {
@@ -1368,6 +1372,10 @@ test_math_kernel(int which, const double* __restrict__ in, size_t n, double* __r
             case 9: y = pgm_lgamma(x); break;
             case 10: y = fm::erfcx_pos(x); break;
             case 11: y = fm::erfcx_pos(x) * fm::exp_neg_sq(x); break;  // erfc(x), x >= 0, as the cdf kernels form it
+            case 20: saddle::lookup(x, y, t); break;                     // Gr(x), tabulated
+            case 21: saddle::lookup(x, t, y); break;                     // Hr(x), tabulated
+            case 22: { double d0, d1; saddle::eval_direct(x, y, d0, t, d1); break; }  // Gr(x), direct solve
+            case 23: { double d0, d1; saddle::eval_direct(x, t, d0, y, d1); break; }  // Hr(x), direct solve
             default: y = fm::div(1.0, x); break;
         }
         out[i] = y;
@@ -1378,6 +1386,7 @@ int
 launch_test_math(int which, const double* d_in, size_t n, double* d_out, cudaStream_t s)
 {
     if (n == 0) return 0;
+    if (int rc = device_init()) return rc;  // (the saddle tables)
     test_math_kernel<<<1184, 256, 0, s>>>(which, d_in, n, d_out);
     count_launch(1);
     return (int)cudaGetLastError();

@@ -324,6 +324,53 @@ def test_small_fill_path_equals_pipeline(pg, torch, monkeypatch, method, compat)
     assert np.array_equal(got_s, want_s)
 
 
+def test_saddle_table(torch):
+    """The tabulated saddle-point functions Gr(x), Hr(x) (csrc/pgm_methods.cuh, namespace saddle) against
+    (i) the kernels' own direct solve at random x and (ii) an independent numpy/scipy solve of
+    K'(u) = x (tanh(s)/s = x or tan(s)/s = x).  The acceptance test multiplies Gr by h <= a few hundred, so
+    1e-10 absolute keeps the acceptance probability within 1e-7 relative."""
+    from polyagamma_b200 import _lib
+    from scipy.optimize import brentq
+
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+
+    def run(which, x):
+        xin = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+        out = torch.empty_like(xin)
+        assert L.pgm_cuda_test_math(which, ctypes.c_void_p(xin.data_ptr()), xin.numel(),
+                                    ctypes.c_void_p(out.data_ptr()), None) == 0
+        return out.cpu().numpy()
+
+    x = np.concatenate([2.0 ** rng.uniform(-5, 3, 400_000), rng.uniform(0.03125, 7.999, 400_000),
+                        np.array([0.03125, 1.0, 1.0 - 2.0**-53, 1.0 + 2.0**-52, 7.999999, 0.5, 2.0, 4.0])])
+    for tab, direct, tol in ((20, 22, 1e-10), (21, 23, 1e-10)):
+        err = np.abs(run(tab, x) - run(direct, x))
+        assert float(err.max()) < tol, (tab, float(err.max()), x[err.argmax()])
+    # outside the table: 0 below 2^-5, the direct solve above 2^3
+    lo = np.array([1e-3, 0.01, 0.031])
+    assert np.all(run(20, lo) == 0.0) and np.all(run(21, lo) == 0.0)
+    assert np.all(np.abs(run(22, lo)) < 1e-13) and np.all(np.abs(run(23, lo)) < 1e-13)
+    hi = np.array([8.0, 11.0, 50.0])
+    assert np.array_equal(run(20, hi), run(22, hi)) and np.array_equal(run(21, hi), run(23, hi))
+
+    # independent reference at a few hundred points
+    def ref(xv):
+        if xv < 1.0:
+            s = brentq(lambda s: np.tanh(s) / s - xv, 1e-9, 1.0 / xv + 1.0, xtol=1e-15, rtol=1e-15)
+            u, c0 = -0.5 * s * s, -(s + np.log1p(np.exp(-2.0 * s)) - np.log(2.0))
+        else:
+            s = brentq(lambda s: np.tan(s) / s - xv, 1e-9, np.pi / 2 - 1e-13, xtol=1e-15, rtol=1e-15)
+            u, c0 = 0.5 * s * s, -np.log(np.cos(s))
+        d = xv * xv + (1.0 - xv) / (2.0 * u)
+        return (c0 - u * xv) + 0.5 / xv - np.log(2.0), 0.5 * np.log(d / xv**3)
+
+    xs = np.concatenate([rng.uniform(0.04, 0.98, 150), rng.uniform(1.02, 7.9, 150)])
+    want = np.array([ref(v) for v in xs])
+    assert float(np.max(np.abs(run(20, xs) - want[:, 0]))) < 1e-9
+    assert float(np.max(np.abs(run(21, xs) - want[:, 1]))) < 1e-9
+
+
 def test_fast_math(torch):
     """The kernels' own elementary functions (fm:: in csrc/pgm_device.cuh) against numpy's libm over
     the argument ranges the samplers produce."""

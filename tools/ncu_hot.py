@@ -20,7 +20,7 @@ ap.add_argument("rep")
 ap.add_argument("kernel")
 ap.add_argument("--top", type=int, default=40)
 ap.add_argument("--lib", default=os.path.join(ROOT, "polyagamma_b200", "libpgm_cuda.so"))
-ap.add_argument("--by", default="line", choices=["line", "file", "window"])
+ap.add_argument("--by", default="line", choices=["line", "file", "window", "func"])
 args = ap.parse_args()
 
 raw = subprocess.run(["ncu", "-i", args.rep, "--page", "source", "--csv", "--print-source", "sass"],
@@ -73,6 +73,36 @@ for f in os.listdir(tmp):
         if m:
             lines.setdefault(int(m.group(1), 16), where)
 
+# enclosing function of a source line (rough: a header line followed by a line that is just "{")
+_func_cache = {}
+
+
+def func_of(fname, line):
+    if fname not in _func_cache:
+        starts = []
+        path = os.path.join(ROOT, "polyagamma_b200", "csrc", fname)
+        if os.path.exists(path):
+            src = open(path).read().splitlines()
+            for i, ln in enumerate(src):
+                if ln.strip() == "{" and i > 0:
+                    for back in range(1, 4):
+                        if i - back < 0:
+                            break
+                        m = re.search(r"([A-Za-z_][A-Za-z_0-9]*)\s*\(", src[i - back])
+                        if m and not src[i - back].rstrip().endswith(";"):
+                            if m.group(1) not in ("if", "for", "while", "switch", "__launch_bounds__"):
+                                starts.append((i - back + 1, m.group(1)))
+                            break
+        _func_cache[fname] = starts
+    name = "?"
+    for st, nm in _func_cache[fname]:
+        if st <= line:
+            name = nm
+        else:
+            break
+    return f"{fname}:{name}"
+
+
 STALLS = [h for h in blk["hdr"] if h.startswith("stall_") and "Not Issued" not in h]
 agg = collections.defaultdict(lambda: collections.Counter())
 total = collections.Counter()
@@ -81,6 +111,8 @@ for r in blk["rows"]:
     where = lines.get(off, ("?", 0))
     if args.by == "file":
         key = where[0]
+    elif args.by == "func":
+        key = func_of(*where)
     elif args.by == "window":
         key = "0x%05x" % (off & ~0x3ff)
     else:
