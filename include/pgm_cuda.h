@@ -17,8 +17,15 @@
  *     NOT an error: it is encoded in the data (h <= 0 or NaN -> NaN, h = +inf -> +inf;
  *     src/pgm_random.c:137-155,162-168).
  *
- * No torch types, no C++ types.  The library allocates only stream-ordered scratch
- * (`cudaMallocAsync`) for the method-bucketing pass; every in/out buffer is caller-owned.
+ * No torch types, no C++ types.  Every in/out buffer is caller-owned.  What the library allocates:
+ *   - per call, stream-ordered scratch from a PRIVATE memory pool of the device (the device's default
+ *     pool is left alone): the element lists and records of the divergent method buckets, 232 B per
+ *     element of a pass (<= 2^25 elements: <= 7.8 GB; the pass is halved while the allocation fails).
+ *     Freed blocks stay cached in that pool; pgm_cuda_release_scratch returns them to the driver;
+ *   - once per device, 80 KB of tables (saddle-point functions) filled by a kernel on a private stream;
+ *     the first call on a device waits for it -- the only host synchronisation on a device-pointer path
+ *     (call pgm_cuda_init before a stream capture to have it out of the way);
+ *   - `_host` entry points only: pinned staging rings, sized by the largest call so far (see there).
  *
  * Threads: every entry point may be called from several host threads at once, each on its own
  * stream (the reference serialises callers with the BitGenerator's lock,
@@ -135,18 +142,24 @@ int pgm_cuda_logistic_omega_step(uint64_t seed, uint64_t offset, const double* d
                                  int method, double* d_gram, double* d_omega, double* d_psi,
                                  uint64_t first_index, void* stream);
 
+/* ---- set-up / tear-down ------------------------------------------------------------------ */
+/* The one-time, per-device initialisation (tables, scratch pool, occupancy of the persistent kernels),
+ * which the first call on a device would otherwise do.  Synchronises a private stream. */
+int pgm_cuda_init(void);
+
 /* ---- introspection ---------------------------------------------------------------------- */
 /* Number of kernels this library has launched in this process (all threads). */
 uint64_t pgm_cuda_launch_count(void);
 /* Per-kernel device time, for roofline accounting.  Between _begin and _end every kernel this
  * library launches is bracketed by CUDA events on its own stream; _end synchronises those
  * events and returns, per kernel kind, the summed milliseconds and the launch count.
- * Kinds: 0 the one-pass bucketing kernel, 1 the one-launch kernel of small fills (2 is unused);
- * sampling kernels 3 devroye (both proposal variants), 4 alternate, 5 saddle (both envelope pieces),
- * 6 saddle-left (left piece only, |z| < 8), 7 saddle-far (left piece, |z| >= 14), 8 alternate-left (left
- * piece only, |z| >= 14), 9 saddle-mid (the far kernel on 8 <= |z| < 14); 10 normal, 11 gamma,
- * 12 density; per-element setup kernels 13..19 in the order of 3..9 (7, 8 and 9 compute their records
- * inside the sampling kernel: no setup launch); 20 psi = X beta, 21 weighted Gram matrix.
+ * Kinds: 0 unused (round 1: the bucketing kernel), 1 the one-launch kernel of small fills, 2 the tile
+ * kernel (classification, the in-tile normal / left-saddle / devroye draws, list compaction);
+ * sampling kernels over a list or an identity range: 3 devroye (both proposal variants), 4 alternate,
+ * 5 saddle (both envelope pieces), 6 saddle-left (left piece only), 7 unused, 8 alternate-left (left
+ * piece only, |z| >= 14), 9 unused; 10 normal, 11 gamma, 12 density; per-element setup kernels 13..19 in
+ * the order of 3..9 (8 computes its records inside the sampling kernel: no setup launch);
+ * 20 psi = X beta, 21 weighted Gram matrix.
  * `cap` = length of both output arrays (>= 22). */
 #define PGM_CUDA_NUM_KERNEL_KINDS 22
 void pgm_cuda_profile_begin(void);
@@ -154,10 +167,13 @@ int pgm_cuda_profile_end(double* ms, uint64_t* launches, int cap);
 /* FP64 (DFMA) peak of the current device in TFLOP/s, measured by a register-resident FMA
  * microbenchmark: the denominator of the FP64 roofline.  Synchronises `stream`. */
 int pgm_cuda_fp64_peak_tflops(double* tflops, void* stream);
-/* The per-pass scratch (up to ~108 B per element of a 2^27-element pass: nine index lists and the records) is allocated stream-ordered
- * from the device's default memory pool and stays cached there between calls.  This returns the
- * cached blocks of the current device to the driver (synchronises the device). */
+/* Returns the cached scratch of the current device (the private pool's free blocks and the `_host`
+ * staging rings) to the driver.  Synchronises the device. */
 int pgm_cuda_release_scratch(void);
+/* Diagnostic: with PGM_CUDA_EVLOG=1 in the environment the fill pipeline records an event after every
+ * operation it enqueues; this prints to stderr which of them the device has not completed (a watchdog can
+ * call it from another thread when a call does not return; tools/stress_probe.py). */
+void pgm_cuda_debug_report(void);
 /* Unit-test hook: applies one of the kernels' own elementary functions (csrc/pgm_device.cuh, fm::)
  * elementwise.  which: 0 rcp, 1 sqrt, 2 log, 3 exp, 4 cos(2 pi x), 5 rsqrt, 9 log Gamma, 10 erfcx (x >= 0), 11 erfc (x >= 0), 6 sin(2 pi x) and
  * 7 cos(2 pi x) of the paired routine, 8 1/x by fm::div. */

@@ -218,9 +218,10 @@ def _method_id(method, ref_compat):
 # ------------------------------------------------------------------------------------------
 # sampling
 # ------------------------------------------------------------------------------------------
-def _fill_scalar_device(seed, offset, h, z, mid, n, device, first_index=0):
+def _fill_scalar_device(seed, offset, h, z, mid, n, device, first_index=0, out=None):
     torch = _torch()
-    out = torch.empty(n, dtype=torch.float64, device=device)
+    if out is None:
+        out = torch.empty(n, dtype=torch.float64, device=device)
     with torch.cuda.device(device):
         rc = _lib.lib().pgm_cuda_random_polyagamma_fill(seed, offset, float(h), float(z), mid, n,
                                                         ctypes.c_void_p(out.data_ptr()), first_index,
@@ -308,13 +309,20 @@ def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable
             if _is_device_array(out):
                 dev = _device_of(out, device=device)
                 ot = _as_device_tensor_view(out, dev)
-                res = _fill_scalar_device(seed, offset, ch, cz, mid, ot.numel(), dev, fi)
-                ot.copy_(res.reshape(ot.shape))
+                torch = _torch()
+                if ot.dtype == torch.float64 and ot.is_contiguous():  # drawn in place
+                    _fill_scalar_device(seed, offset, ch, cz, mid, ot.numel(), dev, fi, out=ot)
+                else:
+                    res = _fill_scalar_device(seed, offset, ch, cz, mid, ot.numel(), dev, fi)
+                    ot.copy_(res.reshape(ot.shape))
                 return out
             arr = _host_out_array(out)
-            dev = _device_of(device=device)
-            res = _fill_scalar_device(seed, offset, ch, cz, mid, arr.size, dev, fi).cpu().numpy()
-            arr[...] = res.reshape(arr.shape)
+            # the pipelined host-buffer entry point with both parameters as one-element operands: the
+            # device->host copies of the result overlap the kernels
+            res = _fill_arrays_host(seed, offset, np.asarray(ch, dtype=np.float64), np.asarray(cz, dtype=np.float64),
+                                    tuple(arr.shape), mid, arr, fi)
+            if res is not arr:
+                arr[...] = res
             return out
         torch = _require_cuda()
         with torch.cuda.device(_device_of(device=device)):

@@ -39,6 +39,8 @@ EXPORTS = (
     "pgm_cuda_fp64_peak_tflops",
     "pgm_cuda_test_math",
     "pgm_cuda_release_scratch",
+    "pgm_cuda_init",
+    "pgm_cuda_debug_report",
     "pgm_cuda_version",
     "pgm_cuda_hybrid_select",
     "pgm_cuda_call_key",
@@ -97,6 +99,10 @@ def lib() -> ctypes.CDLL:
     L.pgm_cuda_fp64_peak_tflops.argtypes = [ctypes.POINTER(d), vp]
     L.pgm_cuda_release_scratch.restype = i
     L.pgm_cuda_release_scratch.argtypes = []
+    L.pgm_cuda_init.restype = i
+    L.pgm_cuda_init.argtypes = []
+    L.pgm_cuda_debug_report.restype = None
+    L.pgm_cuda_debug_report.argtypes = []
     L.pgm_cuda_test_math.restype = i
     L.pgm_cuda_test_math.argtypes = [i, vp, sz, vp, vp]
     L.pgm_cuda_version.restype = ctypes.c_char_p

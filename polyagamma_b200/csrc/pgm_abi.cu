@@ -102,6 +102,18 @@ pgm_cuda_version(void)
     return "polyagamma_b200 0.1.0 sm_100a";
 }
 
+int
+pgm_cuda_init(void)
+{
+    return pgm::device_init();
+}
+
+void
+pgm_cuda_debug_report(void)
+{
+    pgm::evlog_report();
+}
+
 uint64_t
 pgm_cuda_launch_count(void)
 {

@@ -137,12 +137,16 @@ static __constant__ double c_cos[6] = {4.16666666666666019037e-02,  -1.388888888
 constexpr double kLn2Hi = 6.93147180369123816490e-01;
 constexpr double kLn2Lo = 1.90821492927058770002e-10;
 
-// The libdevice fallbacks for arguments outside the lean paths' domain live OUT of line: inlined, each one
-// puts a few KB of never-executed code between the hot instructions of every call site, and the jumps over
-// it defeat the instruction prefetcher (ncu: 80-90 % of the samples at those branches were `no_instruction`).
-static __device__ __noinline__ double slow_sqrt(double x) { return ::sqrt(x); }
-static __device__ __noinline__ double slow_log(double x) { return ::log(x); }
-static __device__ __noinline__ double slow_exp(double x) { return ::exp(x); }
+// The libdevice fallbacks for arguments outside the lean paths' domain.  They are INLINED on purpose.  Out of
+// line (__noinline__: a few KB less never-executed code between the hot instructions of every call site) the
+// persistent sampling kernels hung intermittently -- sample_kernel<Alternate> on chunked elements, one warp
+// never leaving the kernel, once in 2 to 80 calls depending on unrelated code changes, never with the
+// fallbacks inlined (tests/test_gpu_parity.py::test_multi_pass_stress).  Calls into functions with a stack
+// frame from deep inside divergent rejection loops are avoided throughout for that reason; the hot paths use
+// the guard-free log_pn / sqrt_nn below instead.
+static __device__ __forceinline__ double slow_sqrt(double x) { return ::sqrt(x); }
+static __device__ __forceinline__ double slow_log(double x) { return ::log(x); }
+static __device__ __forceinline__ double slow_exp(double x) { return ::exp(x); }
 
 // 1/x for finite normal x: MUFU.RCP64H seed (~20 bits) + two Newton steps
 __device__ __forceinline__ double
@@ -187,11 +191,22 @@ sqrt(double x)
     return fma(fma(-s, s, x), 0.5 * y, s);
 }
 
-// natural logarithm of a finite normal x > 0 (anything else: libdevice)
+// sqrt(x) for finite x >= 0 where an ABSOLUTE error of 1e-150 is harmless (x below 1e-300, zero included, is
+// taken as 1e-300): no special-case branch, so the call site stays one basic block.  NaN in, NaN out.
 __device__ __forceinline__ double
-log(double x)
+sqrt_nn(double x)
 {
-    if (!(x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308)) return slow_log(x);
+    x = (x < 1e-300) ? 1e-300 : x;
+    const double y = rsqrt(x);
+    const double s = x * y;
+    return fma(fma(-s, s, x), 0.5 * y, s);
+}
+
+// natural logarithm of a positive NORMAL finite x -- what the samplers feed it almost everywhere (uniforms in
+// (0, 1], proposals, shapes): no special-case test, the call site stays one basic block.
+__device__ __forceinline__ double
+log_pn(double x)
+{
     const long long bits = __double_as_longlong(x);
     int e = (int)(bits >> 52) - 1023;
     double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);  // [1, 2)
@@ -211,7 +226,16 @@ log(double x)
     return de * kLn2Hi - ((hfsq - (s * (hfsq + R) + de * kLn2Lo)) - f);
 }
 
-// e^x for x <= 700; x < -707 flushes to 0 (the samplers never need denormal results)
+// natural logarithm, any argument (zero, denormal, negative, inf, NaN: libdevice, out of line)
+__device__ __forceinline__ double
+log(double x)
+{
+    if (!(x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308)) return slow_log(x);
+    return log_pn(x);
+}
+
+// e^x for x <= 700; x < -707 flushes to 0 (the samplers never need denormal results), huge or NaN arguments go
+// to libdevice.
 __device__ __forceinline__ double
 exp(double x)
 {
@@ -350,6 +374,25 @@ struct RngT {
         left = 0;
     }
 
+    // Continue the element's stream at word `wpos` (the saddle queue of the tile kernel re-enters a stream
+    // where a rejected proposal left it) / the position reached.
+    __device__ __forceinline__ void seek(uint32_t wpos)
+    {
+        blk = wpos >> 2;
+        left = 0;
+        const uint32_t skip = wpos & 3u;
+        if (skip != 0) {
+            refill_body();
+            for (uint32_t i = 0; i < skip; ++i) {
+                b0 = b1;
+                b1 = b2;
+                b2 = b3;
+            }
+            left = 4 - (int)skip;
+        }
+    }
+    __device__ __forceinline__ uint32_t word_position() const { return 4u * blk - (uint32_t)left; }
+
     // One shared copy of the block function per kernel: u32() has many call sites in the
     // samplers and the persistent kernels live or die by their instruction-cache footprint.
     __device__ __forceinline__ void refill_body()
@@ -398,20 +441,20 @@ struct RngT {
     // (0, 1]
     __device__ __forceinline__ double uniform_oc() { return ((double)u53() + 1.0) * 1.1102230246251565e-16; }
     // replaces numpy random_standard_exponential
-    __device__ __forceinline__ double exponential() { return -fm::log(uniform_oc()); }
+    __device__ __forceinline__ double exponential() { return -fm::log_pn(uniform_oc()); }
     // replaces numpy random_standard_normal: one Box-Muller draw (4 words)
     __device__ __forceinline__ double normal()
     {
         double u1 = uniform_oc();
         double u2 = uniform_co();
-        return fm::sqrt(-2.0 * fm::log(u1)) * fm::cos2pi(u2);
+        return fm::sqrt_nn(-2.0 * fm::log_pn(u1)) * fm::cos2pi(u2);
     }
     // Box-Muller pair (used by the gamma-convolution sampler)
     __device__ __forceinline__ void normal_pair(double& n0, double& n1)
     {
         double u1 = uniform_oc();
         double u2 = uniform_co();
-        double rad = fm::sqrt(-2.0 * fm::log(u1));
+        double rad = fm::sqrt_nn(-2.0 * fm::log_pn(u1));
         double s, c;
         fm::sincos2pi(u2, s, c);
         n0 = rad * c;

@@ -147,7 +147,7 @@ struct DevroyeT {
     {
         double x, lp, e;
         const bool left = s.in_left ? true : (r.uniform_co() < p.w);
-        const double L = -log(r.uniform_oc());
+        const double L = -fm::log_pn(r.uniform_oc());
         if (left) {
             s.in_left = 1;
             constexpr bool pair = LEFT == kDevroyePair;
@@ -163,7 +163,7 @@ struct DevroyeT {
                 const double y2 = 2.0 * L * c * c;
                 const double mu2 = p.mu2;
                 const double w = (p.zz + 0.5 * y2) * mu2;
-                x = mu2 * fm::rcp(w + sqrt(fmax(w * w - mu2, 0.0)));
+                x = mu2 * fm::rcp(w + fm::sqrt_nn(w * w - mu2));
                 if (r.uniform_co() * (1.0 + x * p.zz) > 1.0) {
                     x = mu2 * fm::rcp(x);
                 }
@@ -179,7 +179,7 @@ struct DevroyeT {
             e = 0.5 * kPi * kPi * x;
         }
         else {
-            lp = -1.5 * (kLogPi_2 + log(x));
+            lp = -1.5 * (kLogPi_2 + fm::log_pn(x));
             e = 2.0 * fm::rcp(x);
         }
         double sum = coef(0, lp, e);
@@ -368,7 +368,7 @@ struct Alternate {
         do {
             double y = r.normal();
             double w = p.h_z + 0.5 * y * y * p.inv_z2;
-            x = p.h_z2 * fm::rcp(w + sqrt(fmax(w * w - p.h_z2, 0.0)));
+            x = p.h_z2 * fm::rcp(w + fm::sqrt_nn(w * w - p.h_z2));
             if (r.uniform_co() * (p.h_z + x) > p.h_z) {
                 x = p.h_z2 * fm::rcp(x);
             }
@@ -509,7 +509,7 @@ struct AlternateLeft {
         do {
             double y = r.normal();
             double w = p.h_z + 0.5 * y * y * p.inv_z2;
-            x = p.h_z2 * fm::rcp(w + sqrt(fmax(w * w - p.h_z2, 0.0)));
+            x = p.h_z2 * fm::rcp(w + fm::sqrt_nn(w * w - p.h_z2));
             if (r.uniform_co() * (p.h_z + x) > p.h_z) {
                 x = p.h_z2 * fm::rcp(x);
             }
@@ -720,8 +720,8 @@ constexpr int kTabEmin = -5, kTabEmax = 3;
 constexpr int kTabCells = (kTabEmax - kTabEmin) << kTabBits;
 static __device__ double2 g_saddle_tab[4 * kTabCells];  // per cell: cubic in t of Gr (c0 c1 | c2 c3), then of Hr
 
-// Gr, Hr and their x-derivatives by the direct solve (table generation; x outside the table)
-static __device__ __noinline__ void
+// Gr, Hr and their x-derivatives by the direct solve (table generation; x above the table)
+static __device__ __forceinline__ void
 eval_direct(double x, double& gr, double& dgr, double& hr, double& dhr)
 {
     double u = table_guess(x), f = 0.0, fp = 1.0, fpp = 0.0;
@@ -744,27 +744,52 @@ eval_direct(double x, double& gr, double& dgr, double& hr, double& dhr)
     dhr = 0.5 * (fpp / (fp * fp) - 3.0 * rx);  // dD/dx = K3 du/dx = K3 / K2
 }
 
-__device__ __forceinline__ void
-lookup(double x, double& gr, double& hr)
+// The table lookup in two halves, so that the caller can put independent work (the logarithm of the
+// acceptance uniform) between the loads and their first use.
+struct Lookup {
+    double2 g01, g23, h01, h23;
+    double t;
+    int cell;
+};
+
+__device__ __forceinline__ Lookup
+lookup_issue(double x)
 {
+    Lookup q;
     const int hi = __double2hiint(x);
-    const int cell = (hi >> (20 - kTabBits)) - ((1023 + kTabEmin) << kTabBits);
-    if ((unsigned)cell >= (unsigned)kTabCells) {
+    q.cell = (hi >> (20 - kTabBits)) - ((1023 + kTabEmin) << kTabBits);
+    const int c = min(max(q.cell, 0), kTabCells - 1);  // (out of range: any valid cell, the values are not used)
+    const double x0 = __hiloint2double(hi & ~((1 << (20 - kTabBits)) - 1), 0);                // left end of the cell
+    const double inv_w = __hiloint2double(((2046 + kTabBits) << 20) - (hi & 0x7ff00000), 0);  // 1 / cell width
+    q.t = (x - x0) * inv_w;
+    const double2* p = g_saddle_tab + 4 * c;
+    q.g01 = __ldg(p), q.g23 = __ldg(p + 1), q.h01 = __ldg(p + 2), q.h23 = __ldg(p + 3);
+    return q;
+}
+
+// ABOVE: x may lie above the table (x >= 8: only a right-piece proposal of the full saddle sampler can); the
+// direct solve then runs, inlined (see the note on out-of-line calls in pgm_device.cuh).
+template <bool ABOVE>
+__device__ __forceinline__ void
+lookup_finish(const Lookup& q, double x, double& gr, double& hr)
+{
+    gr = fma(fma(fma(q.g23.y, q.t, q.g23.x), q.t, q.g01.y), q.t, q.g01.x);
+    hr = fma(fma(fma(q.h23.y, q.t, q.h23.x), q.t, q.h01.y), q.t, q.h01.x);
+    if ((unsigned)q.cell >= (unsigned)kTabCells) {
         gr = 0.0;
         hr = 0.0;
-        if (cell > 0) {
+        if (ABOVE && q.cell > 0) {
             double d0, d1;
             eval_direct(x, gr, d0, hr, d1);
         }
-        return;
     }
-    const double x0 = __hiloint2double(hi & ~((1 << (20 - kTabBits)) - 1), 0);                // left end of the cell
-    const double inv_w = __hiloint2double(((2046 + kTabBits) << 20) - (hi & 0x7ff00000), 0);  // 1 / cell width
-    const double t = (x - x0) * inv_w;
-    const double2* c = g_saddle_tab + 4 * cell;
-    const double2 g01 = __ldg(c), g23 = __ldg(c + 1), h01 = __ldg(c + 2), h23 = __ldg(c + 3);
-    gr = fma(fma(fma(g23.y, t, g23.x), t, g01.y), t, g01.x);
-    hr = fma(fma(fma(h23.y, t, h23.x), t, h01.y), t, h01.x);
+}
+
+template <bool ABOVE>
+__device__ __forceinline__ void
+lookup(double x, double& gr, double& hr)
+{
+    lookup_finish<ABOVE>(lookup_issue(x), x, gr, hr);
 }
 
 // invgauss_logcdf (src/pgm_saddle.c:282-292)
@@ -842,7 +867,7 @@ struct SaddleT {
         const double xc = 2.75 * xl;
         const double xl_inv = fm::rcp(xl);
         double gr_c, hr_c;
-        lookup(xc, gr_c, hr_c);
+        lookup<false>(xc, gr_c, hr_c);  // (xc <= 2.75)
         const double slope_l = -0.5 * xl_inv * xl_inv;
         rec[0] = h;
         rec[1] = xl;
@@ -914,11 +939,11 @@ struct SaddleT {
         if (left) {
             const double mu = p.xl, mu2 = p.xl * p.xl;
             do {  // IG(mu = xl, lambda = h) | x < xc, Michael-Schucany-Haas; only the normal's square is needed
-                const double L = -log(r.uniform_oc());
+                const double L = -fm::log_pn(r.uniform_oc());
                 const double c = fm::cos2pi(r.uniform_co());
                 const double y2 = 2.0 * L * c * c;
                 double w = mu + 0.5 * mu2 * y2 * p.inv_h;
-                x = mu2 * fm::rcp(w + sqrt(fmax(w * w - mu2, 0.0)));
+                x = mu2 * fm::rcp(w + fm::sqrt_nn(w * w - mu2));
                 if (r.uniform_co() * (mu + x) > mu) {
                     x = mu2 * fm::rcp(x);
                 }
@@ -927,9 +952,10 @@ struct SaddleT {
         else {
             x = left_bounded_gamma(r, h, -h * p.slope_r, p.xc);
         }
+        const Lookup q = lookup_issue(x);  // (the loads fly while the logarithm is computed)
+        const double lu = fm::log_pn(r.uniform32());
         double gr, hr;
-        lookup(x, gr, hr);
-        const double lu = log(r.uniform32());
+        lookup_finish<FULL>(q, x, gr, hr);
         bool accept;
         if (FULL && x > p.xc) {
             accept = lu + hr + (h + 0.5) * log(x) + h * (p.kappa_r * x + 0.5 * fm::rcp(x)) <= h * gr + p.A_r;
@@ -987,7 +1013,7 @@ normal_approx_sample(R& r, double h, double z)
     // mean + N sqrt(var) with the Box-Muller radius folded into one square root
     const double u1 = r.uniform_oc();
     const double u2 = r.uniform_co();
-    return mean + sqrt(-2.0 * var * log(u1)) * fm::cos2pi(u2);
+    return mean + fm::sqrt_nn(-2.0 * var * fm::log_pn(u1)) * fm::cos2pi(u2);
 }
 
 // random_polyagamma_gamma_conv (src/pgm_random.c:79-97): 200 Marsaglia-Tsang gammas

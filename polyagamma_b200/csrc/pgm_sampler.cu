@@ -13,6 +13,7 @@
 // attempt per loop trip (pgm_methods.cuh); lanes whose element completed are retired and
 // refilled from a per-bucket work counter, found with __ballot_sync/__popc, so a warp never
 // idles on another lane's rejection loop.  Nothing here synchronises the host.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -20,6 +21,39 @@
 #include "pgm_methods.cuh"
 
 namespace pgm {
+
+// Diagnostic (PGM_CUDA_EVLOG=1): an event after every operation the pipeline enqueues, so that a watchdog can
+// ask which of them the device has completed (pgm_cuda_debug_report) without touching the kernels.
+struct LoggedOp {
+    char what[48];
+    cudaEvent_t ev;
+};
+static std::vector<LoggedOp> g_evlog;
+static std::mutex g_evlog_mutex;
+static void
+evlog(const char* what, int k, cudaStream_t st)
+{
+    static const bool on = getenv("PGM_CUDA_EVLOG") != nullptr;
+    if (!on) return;
+    LoggedOp op;
+    snprintf(op.what, sizeof(op.what), "%s %d", what, k);
+    cudaEventCreateWithFlags(&op.ev, cudaEventDisableTiming);
+    cudaEventRecord(op.ev, st);
+    std::lock_guard<std::mutex> lock(g_evlog_mutex);
+    g_evlog.push_back(op);
+}
+void
+evlog_report()
+{
+    std::lock_guard<std::mutex> lock(g_evlog_mutex);
+    size_t done = 0;
+    for (auto& op : g_evlog) done += (cudaEventQuery(op.ev) == cudaSuccess);
+    fprintf(stderr, "[pgm] %zu operations logged, %zu complete; incomplete:\n", g_evlog.size(), done);
+    int shown = 0;
+    for (auto& op : g_evlog) {
+        if (cudaEventQuery(op.ev) != cudaSuccess && shown++ < 12) fprintf(stderr, "[pgm]   %s\n", op.what);
+    }
+}
 
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
@@ -145,8 +179,9 @@ enum : int { kBDevroye = 0, kBAlternate = 1, kBSaddleFull = 2, kBSaddleLeft = 3,
              kBDevroyeMSH = 6, kNumBuckets = 7, kBGamma = 7 };
 constexpr uint32_t kBucketNone = 15;
 
-// ctl layout (uint32): [0..9] bucket counts, [10..19] record bases, [20..29] work counters, [30] ticket
-constexpr int kCtlCount = 0, kCtlBase = 10, kCtlWork = 20, kCtlTicket = 30, kCtlWords = 32;
+// ctl layout of one set of element lists (uint32): [0..9] list lengths by bucket, [10..19] work counters of the
+// buckets' sampling kernels
+constexpr int kCtlCount = 0, kCtlWork = 10, kCtlWords = 32;
 static_assert(kNumBuckets <= 10, "ctl layout");
 
 // (written with selects, not branches: the tile kernel classifies eight elements per thread and the lanes
@@ -220,7 +255,7 @@ struct Bucket {
     const uint32_t* ctl;
     int bucket;
     uint32_t count_imm;
-    double* params;  // record storage for this chunk (kMaxRecordFields doubles per element)
+    double* params;  // record storage (M::kFields doubles per element, structure of arrays)
     int uniform;     // 1: one record (position 0) serves every element (scalar h and z)
 };
 
@@ -238,11 +273,7 @@ view_of(const Bucket& b)
     v.idx = b.idx;
     v.count = b.count_imm;
     v.recs = b.params;
-    if (b.ctl) {
-        uint32_t base = b.ctl[kCtlBase + b.bucket];
-        v.count = b.ctl[kCtlCount + b.bucket];
-        v.recs = b.params + (size_t)base * kMaxRecordFields;
-    }
+    if (b.ctl) v.count = b.ctl[kCtlCount + b.bucket];
     v.stride = b.uniform ? 1u : v.count;
     return v;
 }
@@ -278,31 +309,60 @@ struct LocalRec {
 // ---------------------------------------------------------------------------------------
 // tile kernel: classify + draw the dense buckets in shared memory + compact the rest
 // ---------------------------------------------------------------------------------------
-// One block owns one tile of kTile consecutive elements:
+// A persistent block walks over tiles of kTile consecutive elements.  Per tile:
 //   1. h and z are read ONCE, with 16-byte coalesced loads, into shared memory; every element gets its
-//      bucket (invalid h: the NaN / inf of src/pgm_random.c:137-141 goes straight to the output tile);
-//   2. per-bucket local index lists are built in shared memory (MATCH.ANY groups the lanes of a bucket,
-//      one shared-memory atomic per group);
-//   3. the elements of the divergent buckets are appended, as (index, h, z), to the pass's global lists
-//      (one global atomic per bucket and block reserves the range; stores are contiguous per bucket);
-//   4. the in-tile buckets are drawn from shared memory: the normal approximation densely, two elements
-//      per thread and trip; far saddle and devroye by warps of persistent lanes that retire finished
-//      elements and refill from the tile's list (__ballot_sync/__popc), exactly as sample_kernel does
-//      on a global list;
-//   5. the tile's outputs leave as one coalesced, 16-byte vectorised store.  Positions that belong to a
-//      divergent bucket carry NaN until that bucket's kernel, later in stream order, overwrites them.
+//      bucket (invalid h: the NaN / inf of src/pgm_random.c:137-141 goes straight to the output tile) and
+//      its position in the tile's list of that bucket (MATCH.ANY groups the lanes of a bucket, one
+//      shared-memory atomic per group);
+//   2. the elements of the divergent buckets are appended, as (index, h, z), to the pass's global lists
+//      (one global atomic per bucket and tile reserves the range; stores are contiguous per bucket);
+//   3. the in-tile buckets are drawn from shared memory, the warps of the block moving through the same
+//      phases together (one hot loop at a time in the instruction cache):
+//      - left-only saddle (one proposal per trip, acceptance ~0.9): a QUEUE, not resident lanes.  A round
+//        gives every thread of the block one queued element; a rejected element goes back to the queue as a
+//        record with the word position its Philox stream has reached, and what is left when a tile closes
+//        (less than one round) is carried, as records, into the block's next tile -- so every round but the
+//        block's very last runs with 32 of 32 lanes in every warp (resident lanes left 18-20 of 32 active: a
+//        tile holds ~430 such elements, 1.7 warp-loads per warp);
+//      - devroye (a flattened state machine of several trips per draw): resident lanes that retire finished
+//        elements and refill from the tile's list (__ballot_sync/__popc), drained per tile;
+//      - normal approximation: a work queue of batches of 64 (two elements per lane and trip: their dependency
+//        chains interleave);
+//   4. the tile's outputs leave as one coalesced, 16-byte vectorised store.  Positions that belong to a
+//      divergent bucket, or to a carried saddle element, hold NaN until that bucket's kernel (later in stream
+//      order) or this block (after a later barrier) overwrites them.
 // HBM traffic: 16 B in + 8 B out per element, + 20 B written for each element of a divergent bucket.
 // Which lane draws an element never changes the draw (private Philox stream per element).
-constexpr int kTileThreads = 256;
+#ifndef PGM_TILE_THREADS
+#define PGM_TILE_THREADS 256
+#endif
+// Blocks per SM: 3 (80 registers, no spills on the hot paths) measured faster than 4 (64 registers: 560 B of
+// spills in the saddle round) on cfg4: 25.7 against 29.5 ms per 1e9.
+#ifndef PGM_TILE_BLOCKS_PER_SM
+#define PGM_TILE_BLOCKS_PER_SM (768 / PGM_TILE_THREADS)
+#endif
+constexpr int kTileThreads = PGM_TILE_THREADS;
 constexpr int kTileItems = 8;
 constexpr int kTile = kTileThreads * kTileItems;
+constexpr int kCarryCap = 2 * kTileThreads;  // ring of carried saddle records: < one round + one round's rejects
 #ifndef PGM_TILE_WARP_SHARE
 #define PGM_TILE_WARP_SHARE 128
 #endif
-constexpr uint32_t kTileWarpShare = PGM_TILE_WARP_SHARE;  // list entries per participating warp
-#ifndef PGM_TILE_BLOCKS_PER_SM
-#define PGM_TILE_BLOCKS_PER_SM 4
-#endif
+constexpr uint32_t kTileWarpShare = PGM_TILE_WARP_SHARE;  // devroye list entries per participating warp
+
+struct __align__(16) TileSmem {
+    double hout[kTile];         // h on the way in, the tile's outputs on the way out (an element's h is consumed
+    double z[kTile];            // by the thread that later writes its output)
+    double2 c_hz[kCarryCap];    // ring of saddle records (rejected proposals, elements of closed tiles): (h, z),
+    uint32_t c_idx[kCarryCap];  //   element index inside the pass,
+    uint32_t c_pos[kCarryCap];  //   Philox word position
+    uint16_t list[kTile];       // local indices, grouped by bucket
+    uint32_t cnt[kNumBuckets];    // elements of each bucket in this tile
+    uint32_t off[kNumBuckets];    // start of each bucket's group in list
+    uint32_t gbase[kNumBuckets];  // list buckets: start of this tile's range in the global list
+    uint32_t next[kNumBuckets];   // in-tile buckets: work counter
+    uint32_t c_tail;              // ring: records pushed so far (monotonic; slot = count mod kCarryCap)
+};
 
 // persistent lanes over one in-tile list (same loop as sample_kernel, work counter in shared memory)
 template <class M>
@@ -360,223 +420,337 @@ tile_sample(const FillArgs& a, bool compat, uint64_t index0, const uint16_t* __r
     }
 }
 
+// Two normal-approximation draws, interleaved
+static __device__ __forceinline__ double2
+normal_pair(double h0, double z0, double h1, double z1, uint32_t k0, uint32_t k1, uint64_t i0, uint64_t i1)
+{
+    PhiloxKey key;
+    key.k0 = k0;
+    key.k1 = k1;
+    RngInline r0, r1;
+    r0.init(key, i0);
+    r1.init(key, i1);
+    return make_double2(normal_approx_sample(r0, h0, z0), normal_approx_sample(r1, h1, z1));
+}
+
+// ONE proposal of the left-only saddle sampler for an element whose Philox stream stands at word `wpos`.
+struct SaddleAttempt {
+    double value;
+    uint32_t wpos;
+    bool accepted;
+};
+
+static __device__ __forceinline__ SaddleAttempt
+saddle_attempt(double h, double z, bool compat, uint32_t k0, uint32_t k1, uint64_t index, uint32_t wpos)
+{
+    using M = SaddleLeft;
+    double loc[M::kFields];
+    M::make_record(h, z, compat, loc);
+    M::Par par;
+    M::State st;
+    M::Rng rng;
+    M::load(LocalRec{loc}, par, st, compat);
+    PhiloxKey key;  // (the outlined generator uses k0, k1 only)
+    key.k0 = k0;
+    key.k1 = k1;
+    rng.init(key, index);
+    rng.seek(wpos);
+    SaddleAttempt r;
+    r.accepted = M::step(par, st, rng, compat);
+    r.value = st.acc;
+    r.wpos = rng.word_position();
+    return r;
+}
+
+// One round of the saddle queue.  The queue is the ring's records c_head .. c_tail-1 followed by the tile's
+// first-attempt list entries l_head .. l_count-1; thread t < take takes the t-th queued element and makes ONE
+// proposal.  Accepted: the sample goes to the open tile (shared memory) or, for an element of a closed tile,
+// straight to global memory.  Rejected: back to the ring with the word position the element's Philox stream
+// has reached, so the next attempt continues where this one stopped.  (Block-uniform arguments; the caller
+// puts a barrier between rounds.)
+__device__ __forceinline__ bool
+saddle_round(const FillArgs& a, bool compat, uint32_t tile0, uint32_t tile_n, TileSmem& S, uint32_t take, uint32_t c_head,
+             uint32_t c_count, const uint16_t* __restrict__ list, uint32_t l_head, uint32_t tid, uint32_t lt)
+{
+    const bool mine = tid < take;
+    bool rejected = false;
+    uint32_t idx = 0, wpos = 0, src = 0;  // idx: element index inside the pass; src: where (h, z) came from
+    if (mine) {
+        double h, z;
+        if (tid < c_count) {
+            src = (c_head + tid) % (uint32_t)kCarryCap;
+            const double2 hz = S.c_hz[src];
+            h = hz.x, z = hz.y;
+            idx = S.c_idx[src];
+            wpos = S.c_pos[src];
+            src |= 0x80000000u;
+        }
+        else {
+            src = list[l_head + (tid - c_count)];
+            h = S.hout[src], z = S.z[src];
+            idx = tile0 + src;
+        }
+        const SaddleAttempt r = saddle_attempt(h, z, compat, a.key.k0, a.key.k1, a.first_index + a.base + idx, wpos);
+        if (r.accepted) {
+            // an element of the open tile goes to shared memory, one of a closed tile straight to global memory
+            if (idx - tile0 < tile_n) S.hout[idx - tile0] = r.value;
+            else a.out[a.base + idx] = r.value;
+        }
+        else {
+            rejected = true;
+            wpos = r.wpos;
+        }
+    }
+    const uint32_t rej = __ballot_sync(0xffffffffu, rejected);
+    if (rej != 0) {
+        uint32_t base = 0;
+        const int leader = __ffs(rej) - 1;
+        if ((int)(tid & 31) == leader) base = atomicAdd(&S.c_tail, (uint32_t)__popc(rej));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (rejected) {
+            // (h, z) are read back from where they came from: keeping them live through the proposal costs registers
+            const double2 hz = (src >> 31) ? S.c_hz[src & 0x7fffffffu] : make_double2(S.hout[src], S.z[src]);
+            const uint32_t slot = (base + __popc(rej & lt)) % (uint32_t)kCarryCap;
+            S.c_hz[slot] = hz;
+            S.c_idx[slot] = idx;
+            S.c_pos[slot] = wpos;
+        }
+    }
+    return rejected;
+}
+
 // `method` is the requested sampler (kHybrid: src/pgm_random.c:105-121 decides per element).
-// VEC: h and z are contiguous, 16-byte aligned arrays (or scalars).
+// VEC: h and z are contiguous, 16-byte aligned arrays (or scalars) and every tile of the launch is full.
+// The launch covers tiles tile_first .. tile_first + tile_count - 1 of the pass.
 template <bool VEC>
 __global__ void __launch_bounds__(kTileThreads, PGM_TILE_BLOCKS_PER_SM)
 tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, ElemLists el, uint32_t tile_first,
-            uint32_t tiles_total)
+            uint32_t tile_count)
 {
-    // s_hout: h on the way in, the tile's outputs on the way out (an element's h is consumed by the
-    // thread that later writes its output)
-    __shared__ __align__(16) double s_hout[kTile];
-    __shared__ __align__(16) double s_z[kTile];
-    __shared__ uint16_t s_list[kTile];         // local indices, grouped by bucket
-    __shared__ uint32_t s_cnt[kNumBuckets];    // elements of each bucket in this tile
-    __shared__ uint32_t s_off[kNumBuckets];    // start of each bucket's group in s_list
-    __shared__ uint32_t s_gbase[kNumBuckets];  // list buckets: start of this tile's range in the global list
-    __shared__ uint32_t s_next[kNumBuckets];   // in-tile buckets: work counter
-
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    TileSmem& S = *reinterpret_cast<TileSmem*>(tile_smem);
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t lt = (1u << lane) - 1u;
-    const uint32_t tile0 = (tile_first + blockIdx.x) * kTile;  // first element of the tile inside the pass
-    const uint32_t tn = VEC ? (uint32_t)kTile : min((uint32_t)kTile, n - tile0);
-    const uint64_t g0 = a.base + tile0;
     const bool compat = a.compat != 0;
-    if (tid < kNumBuckets) {
-        s_cnt[tid] = 0;
-        s_next[tid] = 0;
-    }
-    __syncthreads();
+    uint32_t c_head = 0, c_tail = 0;  // ring: records consumed / pushed so far (block-uniform; slot = count mod capacity)
+    if (tid == 0) S.c_tail = 0;       // (the shared copy hands out the slots of a round's pushes)
 
-    // ---- 1. load + classify.  Thread t owns local elements j * 512 + 2 t + {0, 1}, j = 0..3 ----
-    uint32_t where[kTileItems / 2] = {0, 0, 0, 0};  // per owned element: bucket (4 bits) | position in its group (12 bits)
-    {
-        double hv[kTileItems], zv[kTileItems];
-        if (VEC) {
-            if (a.h) {
-                const double2* p = reinterpret_cast<const double2*>(a.h + g0);
-#pragma unroll
-                for (int j = 0; j < kTileItems / 2; ++j) {
-                    const double2 v = __ldg(p + j * kTileThreads + tid);
-                    hv[2 * j] = v.x;
-                    hv[2 * j + 1] = v.y;
-                }
-            }
-            else {
-#pragma unroll
-                for (int k = 0; k < kTileItems; ++k) hv[k] = a.h_scalar;
-            }
-            if (a.z) {
-                const double2* p = reinterpret_cast<const double2*>(a.z + g0);
-#pragma unroll
-                for (int j = 0; j < kTileItems / 2; ++j) {
-                    const double2 v = __ldg(p + j * kTileThreads + tid);
-                    zv[2 * j] = v.x;
-                    zv[2 * j + 1] = v.y;
-                }
-            }
-            else {
-#pragma unroll
-                for (int k = 0; k < kTileItems; ++k) zv[k] = a.z_scalar;
-            }
+    for (uint32_t tile = blockIdx.x; tile < tile_count; tile += gridDim.x) {
+        const uint32_t tile0 = (tile_first + tile) * kTile;  // first element of the tile inside the pass
+        const uint32_t tn = VEC ? (uint32_t)kTile : min((uint32_t)kTile, n - tile0);
+        const uint64_t g0 = a.base + tile0;
+        if (tid < kNumBuckets) {
+            S.cnt[tid] = 0;
+            S.next[tid] = 0;
         }
-        else {
-            // partial tile, or strided / broadcast / unaligned operands: staged through shared memory (one
-            // copy of the general index arithmetic)
+        __syncthreads();
+
+        // ---- 1. load + classify.  Thread t owns local elements j * 2T + 2 t + {0, 1}, j = 0..3 ----
+        uint32_t where[kTileItems / 2] = {0, 0, 0, 0};  // per owned element: bucket (4 bits) | position in its group (12 bits)
+        {
+            double hv[kTileItems], zv[kTileItems];
+            if (VEC) {
+                if (a.h) {
+                    const double2* p = reinterpret_cast<const double2*>(a.h + g0);
+#pragma unroll
+                    for (int j = 0; j < kTileItems / 2; ++j) {
+                        const double2 v = __ldg(p + j * kTileThreads + tid);
+                        hv[2 * j] = v.x;
+                        hv[2 * j + 1] = v.y;
+                    }
+                }
+                else {
+#pragma unroll
+                    for (int k = 0; k < kTileItems; ++k) hv[k] = a.h_scalar;
+                }
+                if (a.z) {
+                    const double2* p = reinterpret_cast<const double2*>(a.z + g0);
+#pragma unroll
+                    for (int j = 0; j < kTileItems / 2; ++j) {
+                        const double2 v = __ldg(p + j * kTileThreads + tid);
+                        zv[2 * j] = v.x;
+                        zv[2 * j + 1] = v.y;
+                    }
+                }
+                else {
+#pragma unroll
+                    for (int k = 0; k < kTileItems; ++k) zv[k] = a.z_scalar;
+                }
+            }
+            else {
+                // partial tile, or strided / broadcast / unaligned operands: staged through shared memory (one
+                // copy of the general index arithmetic)
 #pragma unroll 1
+                for (int k = 0; k < kTileItems; ++k) {
+                    const uint32_t e = (k >> 1) * (2 * kTileThreads) + 2 * tid + (k & 1);
+                    double h = 1.0, z = 0.0;
+                    if (e < tn) load_hz(a, g0 + e, h, z);
+                    S.hout[e] = h;
+                    S.z[e] = z;
+                }
+#pragma unroll
+                for (int j = 0; j < kTileItems / 2; ++j) {
+                    const double2 vh = reinterpret_cast<const double2*>(S.hout)[j * kTileThreads + tid];
+                    const double2 vz = reinterpret_cast<const double2*>(S.z)[j * kTileThreads + tid];
+                    hv[2 * j] = vh.x;
+                    hv[2 * j + 1] = vh.y;
+                    zv[2 * j] = vz.x;
+                    zv[2 * j + 1] = vz.y;
+                }
+            }
+            // Bucket of each element, and its position inside the tile's group of that bucket: the lanes of a
+            // bucket are found with one MATCH.ANY on the bucket id, the lowest lane of a group takes the group's
+            // positions from the bucket's counter in shared memory.
+#pragma unroll
             for (int k = 0; k < kTileItems; ++k) {
                 const uint32_t e = (k >> 1) * (2 * kTileThreads) + 2 * tid + (k & 1);
-                double h = 1.0, z = 0.0;
-                if (e < tn) load_hz(a, g0 + e, h, z);
-                s_hout[e] = h;
-                s_z[e] = z;
+                const double hk = hv[k];
+                // nan_or_inf (src/pgm_random.c:137-141): h <= 0 or NaN -> NaN, +inf -> +inf (h itself)
+                const bool nonpos = !(hk > 0.0);
+                const bool inval = nonpos | (hk == INFINITY);
+                const uint32_t b = (e < tn && !inval) ? classify(method, hk, zv[k], compat) : kBucketNone;
+                hv[k] = nonpos ? NAN : hk;  // invalid h: the output of this element
+                const bool valid = b != kBucketNone;
+                const uint32_t same = __match_any_sync(0xffffffffu, b);
+                const int leader = __ffs(same) - 1;
+                uint32_t r = 0;
+                if (valid && (int)lane == leader) r = atomicAdd(&S.cnt[b], (uint32_t)__popc(same));
+                r = __shfl_sync(0xffffffffu, r, leader) + __popc(same & lt);
+                where[k >> 1] |= (b | (r << 4)) << (16 * (k & 1));
             }
 #pragma unroll
             for (int j = 0; j < kTileItems / 2; ++j) {
-                const double2 vh = reinterpret_cast<const double2*>(s_hout)[j * kTileThreads + tid];
-                const double2 vz = reinterpret_cast<const double2*>(s_z)[j * kTileThreads + tid];
-                hv[2 * j] = vh.x;
-                hv[2 * j + 1] = vh.y;
-                zv[2 * j] = vz.x;
-                zv[2 * j + 1] = vz.y;
+                reinterpret_cast<double2*>(S.hout)[j * kTileThreads + tid] = make_double2(hv[2 * j], hv[2 * j + 1]);
+                reinterpret_cast<double2*>(S.z)[j * kTileThreads + tid] = make_double2(zv[2 * j], zv[2 * j + 1]);
             }
         }
-        // Bucket of each element, and its position inside the tile's group of that bucket: the lanes of a
-        // bucket are found with one MATCH.ANY on the bucket id, the lowest lane of a group takes the group's
-        // positions from the bucket's counter in shared memory.
+        __syncthreads();
+
+        // ---- 2. group offsets; reserve the tile's range in each global list; write the local lists ----
+        if (tid < kNumBuckets) {
+            uint32_t off = 0;
+            for (uint32_t q = 0; q < tid; ++q) off += S.cnt[q];
+            S.off[tid] = off;
+            const uint32_t c = S.cnt[tid];
+            uint32_t base = 0;
+            if (c != 0 && list_slot((int)tid) >= 0) base = atomicAdd(&ctl[kCtlCount + tid], c);
+            S.gbase[tid] = base;
+        }
+        __syncthreads();
 #pragma unroll
         for (int k = 0; k < kTileItems; ++k) {
             const uint32_t e = (k >> 1) * (2 * kTileThreads) + 2 * tid + (k & 1);
-            const double hk = hv[k];
-            // nan_or_inf (src/pgm_random.c:137-141): h <= 0 or NaN -> NaN, +inf -> +inf (h itself)
-            const bool nonpos = !(hk > 0.0);
-            const bool inval = nonpos | (hk == INFINITY);
-            const uint32_t b = (e < tn && !inval) ? classify(method, hk, zv[k], compat) : kBucketNone;
-            hv[k] = nonpos ? NAN : hk;  // invalid h: the output of this element
-            const bool valid = b != kBucketNone;
-            const uint32_t same = __match_any_sync(0xffffffffu, b);
-            const int leader = __ffs(same) - 1;
-            uint32_t r = 0;
-            if (valid && (int)lane == leader) r = atomicAdd(&s_cnt[b], (uint32_t)__popc(same));
-            r = __shfl_sync(0xffffffffu, r, leader) + __popc(same & lt);
-            where[k >> 1] |= (b | (r << 4)) << (16 * (k & 1));
+            const uint32_t w = (where[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+            const uint32_t q = w & 15u;
+            if (q != kBucketNone) S.list[S.off[q] + (w >> 4)] = (uint16_t)e;
         }
-#pragma unroll
-        for (int j = 0; j < kTileItems / 2; ++j) {
-            reinterpret_cast<double2*>(s_hout)[j * kTileThreads + tid] = make_double2(hv[2 * j], hv[2 * j + 1]);
-            reinterpret_cast<double2*>(s_z)[j * kTileThreads + tid] = make_double2(zv[2 * j], zv[2 * j + 1]);
-        }
-    }
-    __syncthreads();
+        __syncthreads();
 
-    // ---- 2. group offsets; reserve the tile's range in each global list; write the local lists ----
-    if (tid < kNumBuckets) {
-        uint32_t off = 0;
-        for (uint32_t q = 0; q < tid; ++q) off += s_cnt[q];
-        s_off[tid] = off;
-        const uint32_t c = s_cnt[tid];
-        uint32_t base = 0;
-        if (c != 0 && list_slot((int)tid) >= 0) base = atomicAdd(&ctl[kCtlCount + tid], c);
-        s_gbase[tid] = base;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kTileItems; ++k) {
-        const uint32_t e = (k >> 1) * (2 * kTileThreads) + 2 * tid + (k & 1);
-        const uint32_t w = (where[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-        const uint32_t q = w & 15u;
-        if (q != kBucketNone) s_list[s_off[q] + (w >> 4)] = (uint16_t)e;
-    }
-    __syncthreads();
-
-    // ---- 3. divergent buckets: append (index, h, z) to the global lists ----
+        // ---- divergent buckets: append (index, h, z) to the global lists ----
 #pragma unroll 1
-    for (int q = 0; q < kNumBuckets; ++q) {
-        const int slot = list_slot(q);
-        if (slot < 0) continue;
-        const uint32_t c = s_cnt[q];
-        if (c == 0) continue;  // block-uniform
-        const uint32_t off = s_off[q];
-        const size_t dst = (size_t)slot * el.stride + s_gbase[q];
-        for (uint32_t i = tid; i < c; i += kTileThreads) {
-            const uint32_t e = s_list[off + i];
-            el.idx[dst + i] = tile0 + e;
-            el.h[dst + i] = s_hout[e];
-            el.z[dst + i] = s_z[e];
-            s_hout[e] = NAN;  // pending: written by the bucket's own kernel
+        for (int q = 0; q < kNumBuckets; ++q) {
+            const int slot = list_slot(q);
+            if (slot < 0) continue;
+            const uint32_t c = S.cnt[q];
+            if (c == 0) continue;  // block-uniform
+            const uint32_t off = S.off[q];
+            const size_t dst = (size_t)slot * el.stride + S.gbase[q];
+            for (uint32_t i = tid; i < c; i += kTileThreads) {
+                const uint32_t e = S.list[off + i];
+                el.idx[dst + i] = tile0 + e;
+                el.h[dst + i] = S.hout[e];
+                el.z[dst + i] = S.z[e];
+                S.hout[e] = NAN;  // pending: written by the bucket's own kernel
+            }
         }
-    }
 
-    // ---- 4. in-tile buckets ----
-    // The expensive lists first (persistent lanes: a warp reserves 32 entries of the tile's list at a time
-    // and refills retired lanes from them), then the normal approximation from a work queue of batches of 64
-    // elements (two per lane: their dependency chains interleave).  Only as many warps as the list can keep
-    // full for a few trips take part in a list (a list of 400 spread over 8 warps leaves every warp with a
-    // half-empty second trip: 18 of 32 lanes); the others start on the queue at once, and a warp that finds a
-    // list exhausted moves on, so the warps of the block reach the barrier below within one item of each other.
-    {
+        // ---- 3. in-tile buckets ----
         const uint64_t index0 = a.first_index + g0;
-        const uint32_t wid = tid >> 5;
-        auto takes_part = [&](uint32_t count) { return wid * kTileWarpShare < count; };
-        if (takes_part(s_cnt[kBSaddleLeft]))
-            tile_sample<SaddleLeft>(a, compat, index0, s_list + s_off[kBSaddleLeft], s_cnt[kBSaddleLeft],
-                                    &s_next[kBSaddleLeft], s_z, s_hout, lane, lt);
-        if (takes_part(s_cnt[kBDevroye]))
-            tile_sample<DevroyeT<kDevroyePair>>(a, compat, index0, s_list + s_off[kBDevroye], s_cnt[kBDevroye],
-                                                &s_next[kBDevroye], s_z, s_hout, lane, lt);
-        if (takes_part(s_cnt[kBDevroyeMSH]))
-            tile_sample<DevroyeT<kDevroyeMSH>>(a, compat, index0, s_list + s_off[kBDevroyeMSH], s_cnt[kBDevroyeMSH],
-                                               &s_next[kBDevroyeMSH], s_z, s_hout, lane, lt);
-        const uint32_t cn = s_cnt[kBNormal];
-        const uint16_t* ln = s_list + s_off[kBNormal];
-        const uint32_t nitems = (cn + 63u) >> 6;
-        for (;;) {
-            uint32_t it = 0;
-            if (lane == 0) it = atomicAdd(&s_next[kBNormal], 1u);
-            it = __shfl_sync(0xffffffffu, it, 0);
-            if (it >= nitems) break;
-            const uint32_t i = (it << 6) + lane;
-            if (i < cn) {
-                const bool two = i + 32u < cn;
-                const uint32_t e0 = ln[i], e1 = two ? ln[i + 32u] : e0;
-                RngInlineRK r0, r1;
-                r0.init(a.key, index0 + e0);
-                r1.init(a.key, index0 + e1);
-                const double v0 = normal_approx_sample(r0, s_hout[e0], s_z[e0]);
-                const double v1 = normal_approx_sample(r1, s_hout[e1], s_z[e1]);
-                if (two) s_hout[e1] = v1;
-                s_hout[e0] = v0;
+        {
+            // saddle queue: full rounds while there is a block-load of work, the rest is carried.  c_tail (how
+            // many records were ever pushed) is tracked in a register as well: a round's barrier counts its
+            // rejections, so the block agrees on the queue length without reading the shared counter.
+            const uint32_t m = S.cnt[kBSaddleLeft];
+            const uint16_t* ls = S.list + S.off[kBSaddleLeft];
+            uint32_t l_head = 0;
+            for (;;) {
+                const uint32_t c_count = c_tail - c_head;
+                if (c_count + (m - l_head) < (uint32_t)kTileThreads) break;
+                const uint32_t from_ring = min(c_count, (uint32_t)kTileThreads);
+                const bool rejected = saddle_round(a, compat, tile0, tn, S, kTileThreads, c_head, from_ring, ls, l_head, tid, lt);
+                c_head += from_ring;
+                l_head += kTileThreads - from_ring;
+                c_tail += (uint32_t)__syncthreads_count(rejected);  // (and the round's pushes are visible)
+            }
+            // close the tile: first-attempt entries that did not fill a round become ring records (their
+            // positions in the output tile keep h until this block, from a later tile, writes the sample)
+            const uint32_t left = m - l_head;
+            if (tid < left) {
+                const uint32_t e = ls[l_head + tid];
+                const uint32_t slot = (c_tail + tid) % (uint32_t)kCarryCap;
+                S.c_hz[slot] = make_double2(S.hout[e], S.z[e]);
+                S.c_idx[slot] = tile0 + e;
+                S.c_pos[slot] = 0;
+            }
+            c_tail += left;
+            if (tid == 0) S.c_tail = c_tail;  // (the next push is at least two barriers away)
+        }
+        {
+            const uint32_t wid = tid >> 5;
+            auto takes_part = [&](uint32_t count) { return wid * kTileWarpShare < count; };
+#ifndef PGM_NO_DEV
+            if (takes_part(S.cnt[kBDevroye]))
+                tile_sample<DevroyeT<kDevroyePair>>(a, compat, index0, S.list + S.off[kBDevroye], S.cnt[kBDevroye],
+                                                    &S.next[kBDevroye], S.z, S.hout, lane, lt);
+            if (takes_part(S.cnt[kBDevroyeMSH]))
+                tile_sample<DevroyeT<kDevroyeMSH>>(a, compat, index0, S.list + S.off[kBDevroyeMSH], S.cnt[kBDevroyeMSH],
+                                                   &S.next[kBDevroyeMSH], S.z, S.hout, lane, lt);
+#endif
+            // normal approximation: work queue of batches of 64 elements
+            const uint32_t cn = S.cnt[kBNormal];
+            const uint16_t* ln = S.list + S.off[kBNormal];
+            const uint32_t nitems = (cn + 63u) >> 6;
+            for (;;) {
+                uint32_t it = 0;
+                if (lane == 0) it = atomicAdd(&S.next[kBNormal], 1u);
+                it = __shfl_sync(0xffffffffu, it, 0);
+                if (it >= nitems) break;
+                const uint32_t i = (it << 6) + lane;
+                if (i < cn) {
+                    const bool two = i + 32u < cn;
+                    const uint32_t e0 = ln[i], e1 = two ? ln[i + 32u] : e0;
+                    const double2 v = normal_pair(S.hout[e0], S.z[e0], S.hout[e1], S.z[e1], a.key.k0, a.key.k1,
+                                                  index0 + e0, index0 + e1);
+                    if (two) S.hout[e1] = v.y;
+                    S.hout[e0] = v.x;
+                }
             }
         }
-    }
-    __syncthreads();
-
-    // ---- 5. the tile's outputs ----
-    double* out = a.out + g0;
-    if (tn == kTile && ((uintptr_t)out & 15) == 0) {
+        __syncthreads();
+        // ---- 4. the tile's outputs ----
+        double* out = a.out + g0;
+        if (tn == (uint32_t)kTile && ((uintptr_t)out & 15) == 0) {
 #pragma unroll
-        for (int j = 0; j < kTileItems / 2; ++j) {
-            reinterpret_cast<double2*>(out)[j * kTileThreads + tid] = reinterpret_cast<const double2*>(s_hout)[j * kTileThreads + tid];
-        }
-    }
-    else {
-        for (uint32_t e = tid; e < tn; e += kTileThreads) out[e] = s_hout[e];
-    }
-
-    // the last block turns the bucket totals into the bases of the packed record regions
-    if (tid == 0) {
-        __threadfence();
-        const uint32_t ticket = atomicAdd(&ctl[kCtlTicket], 1u);
-        if (ticket == tiles_total - 1) {
-            __threadfence();
-            uint32_t base = 0;
-            for (int q = 0; q < kNumBuckets; ++q) {
-                ctl[kCtlBase + q] = base;
-                base += atomicAdd(&ctl[kCtlCount + q], 0u);
+            for (int j = 0; j < kTileItems / 2; ++j) {
+                reinterpret_cast<double2*>(out)[j * kTileThreads + tid] =
+                    reinterpret_cast<const double2*>(S.hout)[j * kTileThreads + tid];
             }
         }
+        else {
+            for (uint32_t e = tid; e < tn; e += kTileThreads) out[e] = S.hout[e];
+        }
+        // (the next tile's first barrier orders these stores before the block's later stores to carried
+        // elements' positions, and before the tile's shared memory is overwritten)
     }
+    // the block's last carried elements: partial rounds until the ring is empty
+    __syncthreads();
+    while (c_tail != c_head) {
+        const uint32_t take = min(c_tail - c_head, (uint32_t)kTileThreads);
+        const bool rejected = saddle_round(a, compat, 0, 0, S, take, c_head, take, nullptr, 0, tid, lt);
+        c_head += take;
+        c_tail += (uint32_t)__syncthreads_count(rejected);
+    }
+
 }
 
 // ---------------------------------------------------------------------------------------
@@ -885,7 +1059,9 @@ device_info()
         for (int i = 0; i < 7; ++i) {
             if (d.blocks_per_sm[i] < 1) d.blocks_per_sm[i] = 1;
         }
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.tile_blocks_per_sm, tile_kernel<true>, kTileThreads, 0);
+        cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+        cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&d.tile_blocks_per_sm, tile_kernel<true>, kTileThreads, sizeof(TileSmem));
         if (d.tile_blocks_per_sm < 1) d.tile_blocks_per_sm = 1;
         cudaStream_t st = nullptr;
         cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
@@ -984,15 +1160,20 @@ launch_method(const DeviceInfo& d, int which, const FillArgs& a, const Bucket& b
               uint32_t* counter, cudaStream_t s)
 {
     const int kind = kKindDevroye + which;
+    const bool debug = getenv("PGM_CUDA_DEBUG") != nullptr;  // diagnostic: synchronise and report after every launch
     if (!FUSED) {
         ScopedKernelTimer timer(kKindSetup + which, s);
         uint64_t nrec = b.uniform ? 1 : count_hint;
         setup_kernel<M><<<grid_for((uint64_t)d.sms * 8, nrec, 256), 256, 0, s>>>(a, b);
+        if (debug) fprintf(stderr, "[pgm] setup_kernel %d -> %d\n", which, (int)cudaStreamSynchronize(s));
+        evlog("setup_kernel", which, s);
     }
     {
         ScopedKernelTimer timer(kind, s);
         sample_kernel<M, FUSED><<<grid_for((uint64_t)d.sms * d.blocks_per_sm[which], count_hint, kPersistThreads),
                                   kPersistThreads, 0, s>>>(a, b, counter);
+        if (debug) fprintf(stderr, "[pgm] sample_kernel %d -> %d\n", which, (int)cudaStreamSynchronize(s));
+        evlog("sample_kernel", which, s);
     }
     count_launch(FUSED ? 1 : 2);
 }
@@ -1006,16 +1187,6 @@ launch_dense(const DeviceInfo& d, const FillArgs& a, const Bucket& b, uint64_t c
     count_launch(1);
 }
 
-// Pass size.  A pass is one tile_kernel launch over up to 2^kChunkLog2Max elements plus the kernels of
-// its divergent buckets.  The one-pass compaction cannot know a list's length before it writes, so the
-// scratch holds one worst-case list per slot: 5 x 20 B per element of a pass (twice with two passes in
-// flight) + one record (72 B) per element: 172 / 272 B per element, 5.8 / 9.1 GB at 2^25.  The pass is
-// halved while the stream-ordered allocation fails.  PGM_CUDA_CHUNK_LOG2 in the environment pins the
-// pass size (tests use it to cross pass seams).
-#ifndef PGM_CHUNK_LOG2_MAX
-#define PGM_CHUNK_LOG2_MAX 25
-#endif
-constexpr int kChunkLog2Min = 20, kChunkLog2Max = PGM_CHUNK_LOG2_MAX;
 constexpr uint64_t kSmallMaxDefault = 1ull << 16;  // mixed-method fills break even near 1e5, single-method ones far later
 
 static int
@@ -1033,15 +1204,6 @@ static int
 env_chunk_log2()
 {
     return env_int("PGM_CUDA_CHUNK_LOG2", 11, 28, 0);  // a pass holds at least one tile; 2^28 entries index with 32 bits
-}
-
-static int
-first_chunk_log2(uint64_t n)
-{
-    if (int forced = env_chunk_log2()) return forced;
-    int lg = kChunkLog2Max;
-    while (lg > kChunkLog2Min && (1ull << (lg - 1)) >= n) --lg;
-    return lg;
 }
 
 static inline size_t
@@ -1068,6 +1230,178 @@ static uint64_t
 multi_min()
 {
     return 1ull << env_int("PGM_CUDA_MULTI_MIN_LOG2", 0, 40, 16);
+}
+
+// fill2 over arrays, n <= 2^31: passes of tile_kernel (caller's stream) + the divergent buckets' kernels (helper
+// streams).  There are two sets of element lists: pass k appends to set k & 1 while the bucket kernels of pass
+// k - 1 drain the other set beside it; the record regions (one per bucket) are shared by the sets, so a
+// bucket's kernels run in launch order on one stream.  Scratch: per set 3 lists x 20 B x pass, + 14 doubles of
+// records x pass (the one-pass compaction cannot know a list's length before it writes, so every list has room
+// for the whole pass): 232 B per element of a pass, 7.8 GB at 2^25; the pass is halved while the stream-ordered
+// allocation fails.  PGM_CUDA_CHUNK_LOG2 in the environment pins the pass size (tests use it to cross pass seams).
+// (Tried and dropped: letting the lists accumulate over several passes and draining them at a threshold, so that
+// the divergent kernels run over millions of elements instead of a few hundred thousand.  It measured 3 % slower
+// on cfg4 -- those kernels are divergence-bound, not tail-bound, and what is left for the forced drain after the
+// last pass has nothing to overlap with.)
+#ifndef PGM_CHUNK_LOG2_MAX
+#define PGM_CHUNK_LOG2_MAX 25
+#endif
+constexpr int kChunkLog2Min = 20, kChunkLog2Max = PGM_CHUNK_LOG2_MAX;
+
+static int
+first_chunk_log2(uint64_t n)
+{
+    if (int forced = env_chunk_log2()) return forced;
+    int lg = kChunkLog2Max;
+    while (lg > kChunkLog2Min && (1ull << (lg - 1)) >= n) --lg;
+    return lg;
+}
+
+static int
+fill_arrays(const DeviceInfo& d, FillArgs a, uint64_t n, int m, cudaStream_t s)
+{
+    cudaError_t err;
+    int lg = first_chunk_log2(n);
+    const bool no_overlap = getenv("PGM_CUDA_NO_OVERLAP") != nullptr;
+    const bool any_buckets = (m != kDevroye);  // explicit devroye is drawn entirely inside the tiles
+    uint64_t chunk = 0;
+    uint32_t cap = 0;
+    size_t list_bytes = 0, rec_bytes = 0;
+    int nsets = 1;
+    const size_t ctl_bytes = align256(kCtlWords * sizeof(uint32_t));
+    constexpr int kRecFields = Alternate::kFields + SaddleFull::kFields;
+    char* ws = nullptr;
+    for (;;) {
+        chunk = 1ull << lg;
+        const uint64_t cmax = n < chunk ? n : chunk;
+        nsets = (n > chunk && !no_overlap && any_buckets) ? 2 : 1;
+        cap = (uint32_t)((cmax + 63) & ~uint64_t(63));
+        list_bytes = any_buckets ? align256((size_t)cap * kNumListSlots * (sizeof(uint32_t) + 2 * sizeof(double))) : 0;
+        rec_bytes = any_buckets ? align256((size_t)cap * kRecFields * sizeof(double)) : 0;
+        err = (cudaError_t)scratch_alloc((void**)&ws, nsets * (ctl_bytes + list_bytes) + rec_bytes, s);
+        if (err == cudaSuccess) break;
+        (void)cudaGetLastError();  // clear the sticky-free allocation error and retry smaller
+        if (err != cudaErrorMemoryAllocation || lg <= kChunkLog2Min || env_chunk_log2()) return (int)err;
+        --lg;
+    }
+    struct ListSet {
+        ElemLists el;
+        uint32_t* ctl;
+    } set[2];
+    for (int i = 0; i < nsets; ++i) {
+        set[i].ctl = (uint32_t*)(ws + (size_t)i * ctl_bytes);
+        char* base = ws + (size_t)nsets * ctl_bytes + (size_t)i * list_bytes;
+        // h and z first (8-byte aligned whatever the capacity), then the indices
+        set[i].el.h = (double*)base;
+        set[i].el.z = set[i].el.h + (size_t)cap * kNumListSlots;
+        set[i].el.idx = (uint32_t*)(set[i].el.z + (size_t)cap * kNumListSlots);
+        set[i].el.stride = cap;
+    }
+    if (nsets == 1) set[1] = set[0];
+    double* rec_alt = (double*)(ws + (size_t)nsets * (ctl_bytes + list_bytes));
+    double* rec_full = rec_alt + (size_t)cap * Alternate::kFields;
+
+    // 16-byte loads in the tile kernel need contiguous, aligned operands (a scalar operand is fine)
+    const bool vec = a.bc.ndim == 0 && (a.h == nullptr || (a.h_stride == 1 && ((uintptr_t)(a.h + a.base) & 15) == 0)) &&
+                     (a.z == nullptr || (a.z_stride == 1 && ((uintptr_t)(a.z + a.base) & 15) == 0));
+    const uint64_t base0 = a.base;
+
+    auto tile_pass = [&](const FillArgs& ap, uint32_t cn, const ListSet& ls, cudaStream_t st) {
+        const uint32_t ntiles = (cn + kTile - 1) / kTile;
+        // full tiles of contiguous, aligned operands take the 16-byte-load kernel; a trailing partial tile (or
+        // every tile, for general operands) the general one
+        const uint32_t nvec = vec ? cn / kTile : 0, ngen = ntiles - nvec;
+        const uint32_t gcap = (uint32_t)d.sms * d.tile_blocks_per_sm;
+        const uint32_t gvec = nvec < gcap ? nvec : gcap, ggen = ngen < gcap ? ngen : gcap;
+        cudaMemsetAsync(ls.ctl, 0, ctl_bytes, st);
+        ScopedKernelTimer timer(kKindTile, st);
+        if (gvec) tile_kernel<true><<<gvec, kTileThreads, sizeof(TileSmem), st>>>(ap, cn, m, ls.ctl, ls.el, 0, nvec);
+        if (ggen) tile_kernel<false><<<ggen, kTileThreads, sizeof(TileSmem), st>>>(ap, cn, m, ls.ctl, ls.el, nvec, ngen);
+        count_launch((gvec ? 1 : 0) + (ggen ? 1 : 0));
+        evlog("tile pass, elements", (int)cn, st);
+    };
+    // The divergent buckets' kernels of one pass.  List lengths stay on the device: the kernels read them
+    // there, so the host never waits for a count (an empty bucket costs one near-empty launch).
+    auto bucket_pass = [&](const FillArgs& ap, const ListSet& ls, cudaStream_t s1, cudaStream_t s2) {
+        auto bucket = [&](int q, double* recs) {
+            const size_t o = (size_t)list_slot(q) * cap;
+            return Bucket{ls.el.idx + o, ls.el.h + o, ls.el.z + o, ls.ctl, q, 0, recs, 0};
+        };
+        if (m == kHybrid || m == kSaddle)
+            launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull, rec_full), cap, ls.ctl + kCtlWork + kBSaddleFull, s2);
+        if (m == kHybrid || m == kAlternate) {
+            launch_method<Alternate>(d, 1, ap, bucket(kBAlternate, rec_alt), cap, ls.ctl + kCtlWork + kBAlternate, s1);
+            launch_method<AlternateLeft, kFuseAltLeft>(d, 5, ap, bucket(kBAlternateLeft, nullptr), cap,
+                                                       ls.ctl + kCtlWork + kBAlternateLeft, s2);
+        }
+    };
+
+    const uint64_t npass = (n + chunk - 1) / chunk;
+    const bool multi = !no_overlap && any_buckets && (nsets == 2 || n >= multi_min());
+    if (!multi) {
+        for (uint64_t k = 0; k < npass; ++k) {
+            const uint64_t off = k * chunk;
+            const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
+            a.base = base0 + off;
+            tile_pass(a, cn, set[0], s);
+            if (any_buckets) bucket_pass(a, set[0], s, s);
+        }
+        cudaFreeAsync(ws, s);
+        return (int)cudaGetLastError();
+    }
+
+    // (the caller's stream `s` may be the null handle of the default stream: compare helpers only)
+    cudaStream_t h1 = helper_stream(0), h2 = helper_stream(1);
+    if (h1 == nullptr || h2 == nullptr) {
+        cudaFreeAsync(ws, s);
+        return (int)cudaErrorUnknown;
+    }
+    // 0-1 tile pass on set, 2-3 helper 1 done with its kernels on set, 4-5 helper 2 likewise.  One set of events
+    // per host thread and device, created once: a wait captures the record that precedes it, so re-recording
+    // an event in the next call cannot disturb the waits of this one, and no other thread touches the set.
+    struct EventSet {
+        cudaEvent_t ev[6];
+        bool ready = false;
+    };
+    static thread_local EventSet t_events[64];
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    EventSet& es = t_events[cur_dev & 63];
+    if (!es.ready) {
+        for (auto& e : es.ev) {
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+                cudaFreeAsync(ws, s);
+                return (int)cudaGetLastError();
+            }
+        }
+        es.ready = true;
+    }
+    cudaEvent_t *ev_tile = es.ev, *ev_d1 = es.ev + 2, *ev_d2 = es.ev + 4;
+    for (uint64_t k = 0; k < npass; ++k) {
+        const int buf = (nsets == 2) ? (int)(k & 1) : 0;
+        const uint64_t off = k * chunk;
+        const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
+        a.base = base0 + off;
+        if (k >= (uint64_t)nsets) {  // the bucket kernels of this set's previous pass are done with it
+            cudaStreamWaitEvent(s, ev_d1[buf], 0);
+            cudaStreamWaitEvent(s, ev_d2[buf], 0);
+        }
+        tile_pass(a, cn, set[buf], s);
+        cudaEventRecord(ev_tile[buf], s);
+        cudaStreamWaitEvent(h1, ev_tile[buf], 0);
+        cudaStreamWaitEvent(h2, ev_tile[buf], 0);
+        bucket_pass(a, set[buf], h1, h2);
+        cudaEventRecord(ev_d1[buf], h1);
+        cudaEventRecord(ev_d2[buf], h2);
+    }
+    // join: each set's last bucket kernels (earlier ones precede them in stream order)
+    for (int b2 = 0; b2 < (npass >= 2 ? nsets : 1); ++b2) {
+        const int buf = (nsets == 2) ? (int)((npass - 1 - b2) & 1) : 0;
+        cudaStreamWaitEvent(s, ev_d1[buf], 0);
+        cudaStreamWaitEvent(s, ev_d2[buf], 0);
+    }
+    cudaFreeAsync(ws, s);
+    return (int)cudaGetLastError();
 }
 
 int
@@ -1149,177 +1483,29 @@ launch_fill(FillArgs a, uint64_t n, int method, cudaStream_t s)
         return (int)cudaGetLastError();
     }
 
-    // per-element parameters (fill2), every other method: passes of tile_kernel + the divergent buckets'
-    // kernels.  With several passes the divergent buckets of pass k (helper streams) run beside the tile
-    // kernel of pass k + 1 (caller's stream); the element lists are double-buffered, the records are not
-    // (the bucket kernels of pass k + 1 wait for all of pass k's).
-    int lg = first_chunk_log2(n);
-    const bool no_overlap = getenv("PGM_CUDA_NO_OVERLAP") != nullptr;
-    uint64_t chunk = 0;
-    size_t list_bytes = 0, par_bytes = 0, prep_bytes = 0;
-    uint32_t list_stride = 0;
-    int nprep = 1;
-    const size_t ctl_bytes = align256(kCtlWords * sizeof(uint32_t));
-    char* ws = nullptr;
-    for (;;) {
-        chunk = 1ull << lg;
-        const uint64_t cmax = n < chunk ? n : chunk;
-        nprep = (n > chunk && !no_overlap) ? 2 : 1;
-        list_stride = (uint32_t)((cmax + 63) & ~uint64_t(63));
-        list_bytes = align256((size_t)list_stride * kNumListSlots * (sizeof(uint32_t) + 2 * sizeof(double)));
-        par_bytes = align256(cmax * kMaxRecordFields * sizeof(double));
-        prep_bytes = list_bytes + ctl_bytes;
-        err = (cudaError_t)scratch_alloc((void**)&ws, nprep * prep_bytes + par_bytes, s);
-        if (err == cudaSuccess) break;
-        (void)cudaGetLastError();  // clear the sticky-free allocation error and retry smaller
-        if (err != cudaErrorMemoryAllocation || lg <= kChunkLog2Min || env_chunk_log2()) return (int)err;
-        --lg;
-    }
-    struct Prep {
-        ElemLists el;
-        uint32_t* ctl;
-    } prep[2];
-    for (int i = 0; i < nprep; ++i) {
-        char* base = ws + (size_t)i * prep_bytes;
-        // h and z first (8-byte aligned whatever the stride), then the indices
-        prep[i].el.h = (double*)base;
-        prep[i].el.z = prep[i].el.h + (size_t)list_stride * kNumListSlots;
-        prep[i].el.idx = (uint32_t*)(prep[i].el.z + (size_t)list_stride * kNumListSlots);
-        prep[i].el.stride = list_stride;
-        prep[i].ctl = (uint32_t*)(base + list_bytes);
-    }
-    if (nprep == 1) prep[1] = prep[0];
-    double* params = (double*)(ws + (size_t)nprep * prep_bytes);
-    const uint64_t cmax_elems = n < chunk ? n : chunk;
-
-    // 16-byte loads in the tile kernel need contiguous, aligned operands (a scalar operand is fine)
-    const bool vec = a.bc.ndim == 0 && (a.h == nullptr || (a.h_stride == 1 && ((uintptr_t)(a.h + a.base) & 15) == 0)) &&
-                     (a.z == nullptr || (a.z_stride == 1 && ((uintptr_t)(a.z + a.base) & 15) == 0));
-    const uint64_t base0 = a.base;
-
-    auto tile_pass = [&](const FillArgs& ap, uint32_t cn, const Prep& pp, cudaStream_t st) {
-        const uint32_t nblocks = (cn + kTile - 1) / kTile;
-        // full tiles of contiguous, aligned operands take the 16-byte-load kernel; a trailing partial tile
-        // (or every tile, for general operands) the general one
-        const uint32_t nvec = vec ? cn / kTile : 0;
-        cudaMemsetAsync(pp.ctl, 0, ctl_bytes, st);
-        {
-            ScopedKernelTimer timer(kKindTile, st);
-            if (nvec) tile_kernel<true><<<nvec, kTileThreads, 0, st>>>(ap, cn, m, pp.ctl, pp.el, 0, nblocks);
-            if (nblocks > nvec)
-                tile_kernel<false><<<nblocks - nvec, kTileThreads, 0, st>>>(ap, cn, m, pp.ctl, pp.el, nvec, nblocks);
-        }
-        count_launch((nvec ? 1 : 0) + (nblocks > nvec ? 1 : 0));
-    };
-    // The divergent buckets of one pass.  Counts and record bases stay on the device: the kernels read
-    // them there, so the host never waits for the histogram (an empty bucket costs one near-empty launch).
-    // The buckets are independent (disjoint elements, disjoint record regions): s1 == s2 serialises them.
-    auto bucket_pass = [&](const FillArgs& ap, uint32_t cn, const Prep& pp, cudaStream_t s1, cudaStream_t s2) {
-        uint32_t* ctl = pp.ctl;
-        auto bucket = [&](int q) {
-            const size_t o = (size_t)list_slot(q) * pp.el.stride;
-            return Bucket{pp.el.idx + o, pp.el.h + o, pp.el.z + o, ctl, q, 0, params, 0};
-        };
-        if (m == kHybrid || m == kSaddle) {
-            launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull), cn, ctl + kCtlWork + kBSaddleFull, s2);
-        }
-        if (m == kHybrid || m == kAlternate) {
-            launch_method<Alternate>(d, 1, ap, bucket(kBAlternate), cn, ctl + kCtlWork + kBAlternate, s1);
-            launch_method<AlternateLeft, kFuseAltLeft>(d, 5, ap, bucket(kBAlternateLeft), cn, ctl + kCtlWork + kBAlternateLeft, s2);
-        }
-    };
-    const bool any_buckets = (m != kDevroye);  // explicit devroye is drawn entirely inside the tiles
-
-    const bool multi = !no_overlap && any_buckets && (nprep == 2 || cmax_elems >= multi_min());
-    if (!multi) {
-        for (uint64_t off = 0; off < n; off += chunk) {
-            const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
-            a.base = base0 + off;
-            tile_pass(a, cn, prep[0], s);
-            if (any_buckets) bucket_pass(a, cn, prep[0], s, s);
-        }
-        cudaFreeAsync(ws, s);
-        return (int)cudaGetLastError();
-    }
-
-    // (the caller's stream `s` may be the null handle of the default stream: compare helpers only)
-    cudaStream_t h1 = helper_stream(0), h2 = helper_stream(1);
-    if (h1 == nullptr || h2 == nullptr) {
-        cudaFreeAsync(ws, s);
-        return (int)cudaErrorUnknown;
-    }
-    // 0-1 tile[buf], 2-3 helper 1 done with pass of parity buf, 4-5 helper 2 likewise.  One set per host
-    // thread and device, created once: a wait captures the record that precedes it, so re-recording an
-    // event in the next call cannot disturb the waits of this one, and no other thread touches the set.
-    struct EventSet {
-        cudaEvent_t ev[6];
-        bool ready = false;
-    };
-    static thread_local EventSet t_events[64];
-    int cur_dev = 0;
-    cudaGetDevice(&cur_dev);
-    EventSet& es = t_events[cur_dev & 63];
-    if (!es.ready) {
-        for (auto& e : es.ev) {
-            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
-                cudaFreeAsync(ws, s);
-                return (int)cudaGetLastError();
-            }
-        }
-        es.ready = true;
-    }
-    cudaEvent_t *ev_tile = es.ev, *ev_d1 = es.ev + 2, *ev_d2 = es.ev + 4;
-    uint64_t k = 0;
-    for (uint64_t off = 0; off < n; off += chunk, ++k) {
-        const int buf = (int)(k & 1);
-        const uint32_t cn = (uint32_t)((n - off) < chunk ? (n - off) : chunk);
-        a.base = base0 + off;
-        if (k >= 2) {  // pass k-2's bucket kernels are done with this set of lists
-            cudaStreamWaitEvent(s, ev_d1[buf], 0);
-            cudaStreamWaitEvent(s, ev_d2[buf], 0);
-        }
-        tile_pass(a, cn, prep[buf], s);
-        cudaEventRecord(ev_tile[buf], s);
-        cudaStreamWaitEvent(h1, ev_tile[buf], 0);
-        cudaStreamWaitEvent(h2, ev_tile[buf], 0);
-        if (k >= 1) {  // the record region is shared: all of pass k-1's bucket kernels first
-            cudaStreamWaitEvent(h1, ev_d2[buf ^ 1], 0);
-            cudaStreamWaitEvent(h2, ev_d1[buf ^ 1], 0);
-        }
-        bucket_pass(a, cn, prep[buf], h1, h2);
-        cudaEventRecord(ev_d1[buf], h1);
-        cudaEventRecord(ev_d2[buf], h2);
-    }
-    // join: the last two passes' bucket kernels (earlier ones precede them in stream order)
-    for (int b2 = 0; b2 < (k >= 2 ? 2 : 1); ++b2) {
-        const int buf = (int)((k - 1 - b2) & 1);
-        cudaStreamWaitEvent(s, ev_d1[buf], 0);
-        cudaStreamWaitEvent(s, ev_d2[buf], 0);
-    }
-    cudaFreeAsync(ws, s);
-    return (int)cudaGetLastError();
+    // per-element parameters (fill2), every other method
+    return fill_arrays(d, a, n, m, s);
 }
 
-// DFMA microbenchmark: the FP64 roofline denominator, measured on the box it is quoted on.
+// DFMA microbenchmark: the FP64 roofline denominator, measured on the box it is quoted on.  Sixteen
+// independent chains per thread (eight left the pipe 8 % short of what tools/dmma_peak.cu reaches: 34.2
+// against 37.0 TFLOP/s).
 __global__ void __launch_bounds__(256)
 dfma_peak_kernel(double* sink, int iters, double b, double c)
 {
-    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
-           a7 = a0 + 7;
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = threadIdx.x + k;
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            a0 = fma(a0, b, c);
-            a1 = fma(a1, b, c);
-            a2 = fma(a2, b, c);
-            a3 = fma(a3, b, c);
-            a4 = fma(a4, b, c);
-            a5 = fma(a5, b, c);
-            a6 = fma(a6, b, c);
-            a7 = fma(a7, b, c);
+        for (int rep = 0; rep < 4; ++rep) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc[k] = fma(acc[k], b, c);
         }
     }
-    double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    double r = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) r += acc[k];
     if (r == 12345.678) sink[0] = r;
 }
 
@@ -1372,8 +1558,8 @@ test_math_kernel(int which, const double* __restrict__ in, size_t n, double* __r
             case 9: y = pgm_lgamma(x); break;
             case 10: y = fm::erfcx_pos(x); break;
             case 11: y = fm::erfcx_pos(x) * fm::exp_neg_sq(x); break;  // erfc(x), x >= 0, as the cdf kernels form it
-            case 20: saddle::lookup(x, y, t); break;                     // Gr(x), tabulated
-            case 21: saddle::lookup(x, t, y); break;                     // Hr(x), tabulated
+            case 20: saddle::lookup<true>(x, y, t); break;               // Gr(x), tabulated
+            case 21: saddle::lookup<true>(x, t, y); break;               // Hr(x), tabulated
             case 22: { double d0, d1; saddle::eval_direct(x, y, d0, t, d1); break; }  // Gr(x), direct solve
             case 23: { double d0, d1; saddle::eval_direct(x, t, d0, y, d1); break; }  // Hr(x), direct solve
             default: y = fm::div(1.0, x); break;

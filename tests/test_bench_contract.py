@@ -33,6 +33,21 @@ def test_reference_arm_prints_one_contract_line(ref):
     assert d["gpu_launches"] == 0
 
 
+@pytest.mark.parametrize("config,unit,elems", [("cfg1", "samples/s", "1000000"), ("cfg2", "samples/s", "20000"),
+                                               ("cfg3-gamma", "samples/s", "2000"), ("cfg3-saddle", "samples/s", "20000"),
+                                               ("cfg5a-pdf", "points/s", "10000"), ("cfg5a-logcdf", "points/s", "2500")])
+def test_reference_arm_covers_every_config(ref, config, unit, elems):
+    """bench.py --config <BASELINE config> --impl reference: the reference's own call for that config."""
+    p = _run("--impl", "reference", "--config", config, "--steps", "1", "--warmup", "1", "--ref-elems", elems)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == unit and d["value"] > 0
+    assert d["config"]["workload"].startswith(config.split("-")[0])
+    assert d["cpu_baseline"]["kind"] == "reference" and d["e2e"]["value"] == d["value"]
+
+
 def test_product_arm_needs_a_gpu():
     import torch
 

@@ -136,6 +136,37 @@ def test_chunk_boundary(pg, torch, monkeypatch):
     torch.cuda.empty_cache()
 
 
+def test_multi_pass_stress(pg, torch, monkeypatch):
+    """Many multi-pass fills back to back (two list sets alternating, bucket kernels on the helper streams beside
+    the next pass's tile kernel, scratch reused from call to call): every call reproduces the single-pass result
+    bit for bit, for the hybrid and for the list-heavy explicit methods."""
+    n = (1 << 20) * 7 + 12345
+    g = torch.Generator(device="cuda")
+    g.manual_seed(77)
+    # plenty of alternate / full-saddle elements (the list buckets)
+    h = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 12 + 0.1
+    z = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 30 - 15
+    cases = ((None, h), ("alternate", h), ("saddle", h + 4))
+    refs = [pg.random_polyagamma(hh, z, method=m, random_state=(9, 3), disable_checks=True) for m, hh in cases]
+    assert all(bool(torch.isfinite(r).all()) for r in refs)
+    for chunk in ("20", "21"):
+        monkeypatch.setenv("PGM_CUDA_CHUNK_LOG2", chunk)
+        for rep in range(6):
+            for (m, hh), ref in zip(cases, refs):
+                got = pg.random_polyagamma(hh, z, method=m, random_state=(9, 3), disable_checks=True)
+                assert torch.equal(got, ref), (chunk, rep, m)
+    # chunked alternate elements (h > 4, |z| < 14) in particular: an earlier build hung here within a few calls
+    hc = h * (8.0 / 12.1) + 4.0
+    ref = pg.random_polyagamma(hc, z, method="alternate", random_state=(9, 4), disable_checks=True)
+    for rep in range(60):
+        got = pg.random_polyagamma(hc, z, method="alternate", random_state=(9, 4), disable_checks=True)
+    assert torch.equal(got, ref)
+    monkeypatch.setenv("PGM_CUDA_NO_OVERLAP", "1")
+    assert torch.equal(pg.random_polyagamma(h, z, random_state=(9, 3), disable_checks=True), refs[0])
+    del h, z, refs, hc, ref, got
+    torch.cuda.empty_cache()
+
+
 def test_hybrid_equals_explicit_methods_full_size(pg, torch):
     """cfg4 at 1e8 elements: the bucketed hybrid result equals, element for element, what each
     explicitly requested method produces on the elements the dispatch rule assigns to it
@@ -403,6 +434,7 @@ def test_fast_math(torch):
     ex = np.concatenate([rng.uniform(-706, 700, n), rng.uniform(-2, 2, n), np.array([0.0, -706.9, 699.9, 1e-300])])
     assert ulps(run(3, ex), np.exp(ex)) <= 2.0
     assert np.array_equal(run(3, np.array([-707.5, -1e4, -np.inf])), np.zeros(3))
+    assert np.isinf(run(3, np.array([710.5, np.inf]))).all() and np.isnan(run(3, np.array([np.nan]))[0])
     u = np.concatenate([rng.random(n), np.array([0.0, 0.25, 0.5, 0.75, 1.0, 0.125, 1 - 2.0**-53])])
     for which, ref in ((4, np.cos), (7, np.cos), (6, np.sin)):
         assert float(np.max(np.abs(run(which, u) - ref(2 * np.pi * u)))) <= 1e-15
