@@ -442,37 +442,6 @@ dev_setup(dev_par* p, double z)
     }
 }
 
-/* random_right_bounded_invgauss (src/pgm_devroye.c:113-142): IG(1/z, 1) | x < T */
-static double
-dev_trunc_invgauss(pgo_rng* r, const dev_par* p)
-{
-    double x;
-    if (p->zz < 1.5625) { /* 1/T */
-        for (;;) {
-            double e1, e2;
-            do {
-                e1 = rng_exponential(r);
-                e2 = rng_exponential(r);
-            } while (e1 * e1 > 3.125 * e2); /* 2/T */
-            x = 1.0 + PGO_T * e1;
-            x = PGO_T / (x * x);
-            if (!(p->zz > 0.0)) break;
-            if (rng_uniform32(r) < exp(-0.5 * p->z2 * x)) break;
-        }
-        return x;
-    }
-    double mu2 = 1.0 / p->z2;
-    do { /* Michael, Schucany & Haas; smaller root written without cancellation */
-        double y = rng_normal(r);
-        double w = (p->zz + 0.5 * y * y) * mu2;
-        x = mu2 / (w + sqrt(fmax(w * w - mu2, 0.0)));
-        if (rng_uniform_co(r) * (1.0 + x * p->zz) > 1.0) {
-            x = mu2 / x;
-        }
-    } while (x >= PGO_T);
-    return x;
-}
-
 /* piecewise_coef (src/pgm_devroye.c:36-46): a_n(x) = pi (n+1/2) exp(lp - e (n+1/2)^2) */
 static double
 dev_coef(int n, double lp, double e)
@@ -481,17 +450,60 @@ dev_coef(int n, double lp, double e)
     return PGO_PI * a * exp(lp - e * a * a);
 }
 
-/* random_jacobi_star (src/pgm_devroye.c:160-190) */
+static double
+u53_from(uint32_t lo, uint32_t hi)
+{
+    return (double)(((((uint64_t)hi) << 32) | lo) >> 11);
+}
+
+/* random_jacobi_star (src/pgm_devroye.c:160-190) with random_right_bounded_invgauss (:113-142) inside,
+ * written as the kernels run it: a sequence of TRIPS, each consuming exactly EIGHT words (two Philox blocks)
+ * of the element's stream whatever it does with them --
+ *     w0 w1   mixture uniform (53 bits, [0, 1)); ignored while a truncated inverse-Gaussian draw is being retried
+ *     w2 w3   L = -log U, U 53 bits in (0, 1]: the tail exponential, the first exponential of Devroye's pair, or
+ *             half the squared Box-Muller radius of the Michael-Schucany-Haas normal
+ *     w4 w5   the pair's second exponential, or the Box-Muller angle
+ *     w6      32-bit uniform: the exponential-tilt test of the pair proposal, or the root choice of M-S-H
+ *     w7      32-bit uniform of the alternating-series test
+ * -- so that all lanes of a warp generate their two blocks together at the top of a trip (a lane that refills
+ * its four-word buffer whenever it runs dry does so alone: 11 of 32 lanes active in the Philox rounds, a
+ * quarter of the kernel's instructions).  A trip ends in: a retry of the left piece (the nested loops of the
+ * reference, flattened), a rejected proposal, or an accepted J*(1, z) draw. */
 static double
 dev_jacobi_star(pgo_rng* r, const dev_par* p)
 {
+    int in_left = 0;
     for (;;) {
+        uint32_t w[8];
+        for (int k = 0; k < 8; ++k) w[k] = rng_u32(r);
         double x, lp, e;
-        if (rng_uniform_co(r) < p->w) {
-            x = dev_trunc_invgauss(r, p);
+        const int left = in_left ? 1 : (u53_from(w[0], w[1]) * 1.1102230246251565e-16 < p->w);
+        const double L = -log((u53_from(w[2], w[3]) + 1.0) * 1.1102230246251565e-16);
+        const double u6 = ((double)w[6] + 0.5) * 2.3283064365386963e-10;
+        if (left) {
+            in_left = 1;
+            if (p->zz < 1.5625) { /* 1/T: exponential-pair proposal of Devroye (2009) */
+                const double e2 = -log((u53_from(w[4], w[5]) + 1.0) * 1.1102230246251565e-16);
+                if (L * L > 3.125 * e2) continue; /* 2/T */
+                x = 1.0 + PGO_T * L;
+                x = PGO_T / (x * x);
+                if (p->zz > 0.0 && !(u6 < exp(-0.5 * p->z2 * x))) continue;
+            }
+            else { /* Michael, Schucany & Haas; smaller root written without cancellation */
+                const double c = cos(2.0 * PGO_PI * (u53_from(w[4], w[5]) * 1.1102230246251565e-16));
+                const double y2 = 2.0 * L * c * c;
+                const double mu2 = 1.0 / p->z2;
+                const double ww = (p->zz + 0.5 * y2) * mu2;
+                x = mu2 / (ww + sqrt(fmax(ww * ww - mu2, 0.0)));
+                if (u6 * (1.0 + x * p->zz) > 1.0) {
+                    x = mu2 / x;
+                }
+                if (x >= PGO_T) continue;
+            }
+            in_left = 0;
         }
         else {
-            x = PGO_T + rng_exponential(r) / p->K;
+            x = PGO_T + L / p->K;
         }
         if (x > PGO_T) {
             lp = 0.0;
@@ -502,7 +514,7 @@ dev_jacobi_star(pgo_rng* r, const dev_par* p)
             e = 2.0 / x;
         }
         double s = dev_coef(0, lp, e);
-        double u = rng_uniform32(r) * s;
+        double u = (((double)w[7] + 0.5) * 2.3283064365386963e-10) * s;
         s -= dev_coef(1, lp, e);
         if (u <= s) return x;
         int rejected = 0;

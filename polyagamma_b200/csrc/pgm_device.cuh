@@ -374,6 +374,43 @@ struct RngT {
         left = 0;
     }
 
+    // The next TWO blocks of the stream at once (the stream must stand at a block boundary: a sampler that
+    // uses this draws all its words this way).  Every lane of a warp generates its blocks together, and the
+    // two sets of rounds interleave.
+    __device__ __forceinline__ void two_blocks(uint32_t (&w)[8])
+    {
+        w[0] = i0, w[1] = i1, w[2] = blk, w[3] = 0;
+        w[4] = i0, w[5] = i1, w[6] = blk + 1, w[7] = 0;
+        uint32_t ka = k0, kb = k1;
+#pragma unroll
+        for (int rnd = 0; rnd < 10; ++rnd) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 4) {
+                const uint64_t p0 = (uint64_t)0xD2511F53u * w[j], p1 = (uint64_t)0xCD9E8D57u * w[j + 2];
+                const uint32_t n0 = (uint32_t)(p1 >> 32) ^ w[j + 1] ^ ka, n2 = (uint32_t)(p0 >> 32) ^ w[j + 3] ^ kb;
+                w[j] = n0;
+                w[j + 1] = (uint32_t)p1;
+                w[j + 2] = n2;
+                w[j + 3] = (uint32_t)p0;
+            }
+            ka += 0x9E3779B9u;
+            kb += 0xBB67AE85u;
+        }
+        blk += 2;
+    }
+    static __device__ __forceinline__ double to_co(uint32_t lo, uint32_t hi)  // 53 bits, [0, 1)
+    {
+        return (double)((((uint64_t)hi << 32) | lo) >> 11) * 1.1102230246251565e-16;
+    }
+    static __device__ __forceinline__ double to_oc(uint32_t lo, uint32_t hi)  // 53 bits, (0, 1]
+    {
+        return ((double)((((uint64_t)hi << 32) | lo) >> 11) + 1.0) * 1.1102230246251565e-16;
+    }
+    static __device__ __forceinline__ double to_u32(uint32_t w)  // 32 bits, (0, 1)
+    {
+        return ((double)w + 0.5) * 2.3283064365386963e-10;
+    }
+
     // Continue the element's stream at word `wpos` (the saddle queue of the tile kernel re-enters a stream
     // where a rejected proposal left it) / the position reached.
     __device__ __forceinline__ void seek(uint32_t wpos)

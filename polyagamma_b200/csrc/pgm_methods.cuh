@@ -139,32 +139,36 @@ struct DevroyeT {
     // One trip of random_jacobi_star (src/pgm_devroye.c:160-190) with the retry loops of
     // random_right_bounded_invgauss (:113-142) FLATTENED into the trip: a lane whose exponential
     // pair / Michael-Schucany-Haas draw fails returns with in_left set and simply proposes again
-    // next trip (same draw order as the nested loops of the oracle), instead of spinning while
-    // the other 31 lanes wait.  All three proposal kinds start from the same quantity
-    // L = -log(U): the tail exponential, the first exponential of the pair, half the squared
-    // Box-Muller radius -- so that logarithm is computed once, convergently.
+    // next trip, instead of spinning while the other 31 lanes wait.  A trip consumes exactly EIGHT words of
+    // the element's stream (two Philox blocks, generated by all lanes together at its top; oracle/pgm_oracle.c
+    // dev_jacobi_star states which word is what): lanes that refill a four-word buffer whenever it runs dry do
+    // so alone -- 11 of 32 lanes active in the Philox rounds, a quarter of the kernel's instructions.  All three
+    // proposal kinds start from the same quantity L = -log(U): the tail exponential, the first exponential of
+    // the pair, half the squared Box-Muller radius -- so that logarithm is computed once, convergently.
     static __device__ __forceinline__ bool step(Par& p, State& s, Rng& r, bool)
     {
+        uint32_t w[8];
+        r.two_blocks(w);
         double x, lp, e;
-        const bool left = s.in_left ? true : (r.uniform_co() < p.w);
-        const double L = -fm::log_pn(r.uniform_oc());
+        const bool left = s.in_left ? true : (Rng::to_co(w[0], w[1]) < p.w);
+        const double L = -fm::log_pn(Rng::to_oc(w[2], w[3]));
         if (left) {
             s.in_left = 1;
             constexpr bool pair = LEFT == kDevroyePair;
             if (pair) {  // |z|/2 < 1/T: exponential-pair proposal of Devroye (2009)
-                const double e2 = r.exponential();
+                const double e2 = -fm::log_pn(Rng::to_oc(w[4], w[5]));
                 if (L * L > 3.125 * e2) return false;
                 x = 1.0 + T * L;
                 x = T * fm::rcp(x * x);
-                if (p.zz > 0.0 && !(r.uniform32() < exp(-0.5 * p.z2 * x))) return false;
+                if (p.zz > 0.0 && !(Rng::to_u32(w[6]) < exp(-0.5 * p.z2 * x))) return false;
             }
             else {  // IG(1/z, 1) by Michael-Schucany-Haas; only the square of the normal is needed
-                const double c = fm::cos2pi(r.uniform_co());
+                const double c = fm::cos2pi(Rng::to_co(w[4], w[5]));
                 const double y2 = 2.0 * L * c * c;
                 const double mu2 = p.mu2;
-                const double w = (p.zz + 0.5 * y2) * mu2;
-                x = mu2 * fm::rcp(w + fm::sqrt_nn(w * w - mu2));
-                if (r.uniform_co() * (1.0 + x * p.zz) > 1.0) {
+                const double ww = (p.zz + 0.5 * y2) * mu2;
+                x = mu2 * fm::rcp(ww + fm::sqrt_nn(ww * ww - mu2));
+                if (Rng::to_u32(w[6]) * (1.0 + x * p.zz) > 1.0) {
                     x = mu2 * fm::rcp(x);
                 }
                 if (x >= T) return false;
@@ -183,7 +187,7 @@ struct DevroyeT {
             e = 2.0 * fm::rcp(x);
         }
         double sum = coef(0, lp, e);
-        double u = r.uniform32() * sum;
+        double u = Rng::to_u32(w[7]) * sum;
         sum -= coef(1, lp, e);
         bool accept = (u <= sum);
         if (!accept) {

@@ -217,12 +217,15 @@ classify(int method, double h, double z, bool compat)
     return (method == kHybrid) ? hyb : expl;
 }
 
-// Where a bucket's elements are drawn.  The near-dense, short-setup buckets (normal approximation,
-// left-only saddle, both devroye proposals: 96 % of cfg4, all of cfg2) are drawn INSIDE tile_kernel, from
-// shared memory, and their outputs leave the SM as part of the tile's coalesced store.  The divergent
-// buckets go to global element lists: slot s of the pass's ElemLists holds (index, h, z) of its
-// elements, compacted, so the per-method kernels read contiguously instead of gathering 8-byte
-// operands through 32-byte sectors.
+// Where a bucket's elements are drawn.  The near-dense buckets whose proposals cost about the same for every
+// element (normal approximation, left-only saddle: 96 % of cfg4) are drawn INSIDE tile_kernel, from shared
+// memory, and their outputs leave the SM as part of the tile's coalesced store.  The others go to global
+// element lists: slot s of the pass's ElemLists holds (index, h, z) of its elements, compacted, so the
+// per-method kernels read contiguously instead of gathering 8-byte operands through 32-byte sectors.
+// (devroye was drawn in the tiles for a while: its flattened state machine needs resident lanes, and a tile's
+// list is too short for them -- every tile ended in a drain at 16 of 32 lanes, cfg2 ran at 8.7e9 samples/s
+// against 1.5e10 with one persistent kernel over the whole pass, and its registers cost the tile kernel a
+// fourth resident block.)
 __host__ __device__ __forceinline__ int
 list_slot(int bucket)
 {
@@ -230,10 +233,12 @@ list_slot(int bucket)
         case kBAlternate: return 0;
         case kBSaddleFull: return 1;
         case kBAlternateLeft: return 2;
+        case kBDevroye: return 3;
+        case kBDevroyeMSH: return 4;
         default: return -1;  // drawn in the tile
     }
 }
-constexpr int kNumListSlots = 3;
+constexpr int kNumListSlots = 5;
 
 struct ElemLists {
     uint32_t* idx;  // slot s: idx + s * stride, h + s * stride, z + s * stride
@@ -336,19 +341,15 @@ struct LocalRec {
 #ifndef PGM_TILE_THREADS
 #define PGM_TILE_THREADS 256
 #endif
-// Blocks per SM: 3 (80 registers, no spills on the hot paths) measured faster than 4 (64 registers: 560 B of
-// spills in the saddle round) on cfg4: 25.7 against 29.5 ms per 1e9.
+// Blocks per SM: 4 (64 registers, 16 B of spills).  While devroye was drawn in the tiles the kernel needed 80
+// registers to stay out of local memory and ran 3 blocks per SM (cfg4 tile time 24.3 ms per 1e9; 22.9 now).
 #ifndef PGM_TILE_BLOCKS_PER_SM
-#define PGM_TILE_BLOCKS_PER_SM (768 / PGM_TILE_THREADS)
+#define PGM_TILE_BLOCKS_PER_SM (1024 / PGM_TILE_THREADS)
 #endif
 constexpr int kTileThreads = PGM_TILE_THREADS;
 constexpr int kTileItems = 8;
 constexpr int kTile = kTileThreads * kTileItems;
 constexpr int kCarryCap = 2 * kTileThreads;  // ring of carried saddle records: < one round + one round's rejects
-#ifndef PGM_TILE_WARP_SHARE
-#define PGM_TILE_WARP_SHARE 128
-#endif
-constexpr uint32_t kTileWarpShare = PGM_TILE_WARP_SHARE;  // devroye list entries per participating warp
 
 struct __align__(16) TileSmem {
     double hout[kTile];         // h on the way in, the tile's outputs on the way out (an element's h is consumed
@@ -363,62 +364,6 @@ struct __align__(16) TileSmem {
     uint32_t next[kNumBuckets];   // in-tile buckets: work counter
     uint32_t c_tail;              // ring: records pushed so far (monotonic; slot = count mod kCarryCap)
 };
-
-// persistent lanes over one in-tile list (same loop as sample_kernel, work counter in shared memory)
-template <class M>
-__device__ __forceinline__ void
-tile_sample(const FillArgs& a, bool compat, uint64_t index0, const uint16_t* __restrict__ list, uint32_t count,
-            uint32_t* s_next, const double* s_z, double* s_hout, uint32_t lane, uint32_t lt)
-{
-    if (count == 0) return;  // block-uniform
-    typename M::Par par;
-    typename M::State st;
-    typename M::Rng rng;
-    uint32_t e = 0;
-    bool active = false;
-    uint32_t wnext = 0, wend = 0;
-    bool exhausted = false;
-    for (;;) {
-        const uint32_t need = __ballot_sync(0xffffffffu, !active);
-        if (need != 0 && !(exhausted && wnext == wend)) {
-            if (wnext == wend) {
-                uint32_t w = 0;
-                if (lane == 0) w = atomicAdd(s_next, 32u);
-                w = __shfl_sync(0xffffffffu, w, 0);
-                if (w >= count) {
-                    exhausted = true;
-                }
-                else {
-                    wnext = w;
-                    wend = min(w + 32u, count);
-                }
-            }
-            if (wnext < wend) {
-                const uint32_t pos = wnext + __popc(need & lt);
-                if (!active && pos < wend) {
-                    e = list[pos];
-                    double loc[M::kFields];
-                    M::make_record(s_hout[e], s_z[e], compat, loc);
-                    if (M::load(LocalRec{loc}, par, st, compat)) {
-                        rng.init(a.key, index0 + e);
-                        active = true;
-                    }
-                    else {
-                        s_hout[e] = 0.0;  // nothing to draw (devroye with floor(h) == 0)
-                    }
-                }
-                wnext = min(wnext + (uint32_t)__popc(need), wend);
-            }
-        }
-        if (active) {
-            if (M::step(par, st, rng, compat)) {
-                s_hout[e] = st.acc;
-                active = false;
-            }
-        }
-        if (exhausted && wnext == wend && !__any_sync(0xffffffffu, active)) break;
-    }
-}
 
 // Two normal-approximation draws, interleaved
 static __device__ __forceinline__ double2
@@ -550,7 +495,7 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
         {
             double hv[kTileItems], zv[kTileItems];
             if (VEC) {
-                if (a.h) {
+                if (a.h != nullptr && a.h_stride != 0) {
                     const double2* p = reinterpret_cast<const double2*>(a.h + g0);
 #pragma unroll
                     for (int j = 0; j < kTileItems / 2; ++j) {
@@ -559,11 +504,12 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
                         hv[2 * j + 1] = v.y;
                     }
                 }
-                else {
+                else {  // one value for the whole call: a host scalar, or a one-element device operand
+                    const double v = a.h ? __ldg(a.h) : a.h_scalar;
 #pragma unroll
-                    for (int k = 0; k < kTileItems; ++k) hv[k] = a.h_scalar;
+                    for (int k = 0; k < kTileItems; ++k) hv[k] = v;
                 }
-                if (a.z) {
+                if (a.z != nullptr && a.z_stride != 0) {
                     const double2* p = reinterpret_cast<const double2*>(a.z + g0);
 #pragma unroll
                     for (int j = 0; j < kTileItems / 2; ++j) {
@@ -573,8 +519,9 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
                     }
                 }
                 else {
+                    const double v = a.z ? __ldg(a.z) : a.z_scalar;
 #pragma unroll
-                    for (int k = 0; k < kTileItems; ++k) zv[k] = a.z_scalar;
+                    for (int k = 0; k < kTileItems; ++k) zv[k] = v;
                 }
             }
             else {
@@ -696,16 +643,6 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
             if (tid == 0) S.c_tail = c_tail;  // (the next push is at least two barriers away)
         }
         {
-            const uint32_t wid = tid >> 5;
-            auto takes_part = [&](uint32_t count) { return wid * kTileWarpShare < count; };
-#ifndef PGM_NO_DEV
-            if (takes_part(S.cnt[kBDevroye]))
-                tile_sample<DevroyeT<kDevroyePair>>(a, compat, index0, S.list + S.off[kBDevroye], S.cnt[kBDevroye],
-                                                    &S.next[kBDevroye], S.z, S.hout, lane, lt);
-            if (takes_part(S.cnt[kBDevroyeMSH]))
-                tile_sample<DevroyeT<kDevroyeMSH>>(a, compat, index0, S.list + S.off[kBDevroyeMSH], S.cnt[kBDevroyeMSH],
-                                                   &S.next[kBDevroyeMSH], S.z, S.hout, lane, lt);
-#endif
             // normal approximation: work queue of batches of 64 elements
             const uint32_t cn = S.cnt[kBNormal];
             const uint16_t* ln = S.list + S.off[kBNormal];
@@ -1263,7 +1200,7 @@ fill_arrays(const DeviceInfo& d, FillArgs a, uint64_t n, int m, cudaStream_t s)
     cudaError_t err;
     int lg = first_chunk_log2(n);
     const bool no_overlap = getenv("PGM_CUDA_NO_OVERLAP") != nullptr;
-    const bool any_buckets = (m != kDevroye);  // explicit devroye is drawn entirely inside the tiles
+    const bool any_buckets = true;
     uint64_t chunk = 0;
     uint32_t cap = 0;
     size_t list_bytes = 0, rec_bytes = 0;
@@ -1302,8 +1239,10 @@ fill_arrays(const DeviceInfo& d, FillArgs a, uint64_t n, int m, cudaStream_t s)
     double* rec_full = rec_alt + (size_t)cap * Alternate::kFields;
 
     // 16-byte loads in the tile kernel need contiguous, aligned operands (a scalar operand is fine)
-    const bool vec = a.bc.ndim == 0 && (a.h == nullptr || (a.h_stride == 1 && ((uintptr_t)(a.h + a.base) & 15) == 0)) &&
-                     (a.z == nullptr || (a.z_stride == 1 && ((uintptr_t)(a.z + a.base) & 15) == 0));
+    auto vec_ok = [&](const double* p, int64_t stride) {
+        return p == nullptr || stride == 0 || (stride == 1 && ((uintptr_t)(p + a.base) & 15) == 0);
+    };
+    const bool vec = a.bc.ndim == 0 && vec_ok(a.h, a.h_stride) && vec_ok(a.z, a.z_stride);
     const uint64_t base0 = a.base;
 
     auto tile_pass = [&](const FillArgs& ap, uint32_t cn, const ListSet& ls, cudaStream_t st) {
@@ -1333,6 +1272,11 @@ fill_arrays(const DeviceInfo& d, FillArgs a, uint64_t n, int m, cudaStream_t s)
             launch_method<Alternate>(d, 1, ap, bucket(kBAlternate, rec_alt), cap, ls.ctl + kCtlWork + kBAlternate, s1);
             launch_method<AlternateLeft, kFuseAltLeft>(d, 5, ap, bucket(kBAlternateLeft, nullptr), cap,
                                                        ls.ctl + kCtlWork + kBAlternateLeft, s2);
+        }
+        if (m == kHybrid || m == kDevroye) {
+            launch_method<DevroyeT<kDevroyePair>, true>(d, 0, ap, bucket(kBDevroye, nullptr), cap, ls.ctl + kCtlWork + kBDevroye, s1);
+            launch_method<DevroyeT<kDevroyeMSH>, true>(d, 0, ap, bucket(kBDevroyeMSH, nullptr), cap,
+                                                       ls.ctl + kCtlWork + kBDevroyeMSH, s2);
         }
     };
 
