@@ -62,8 +62,9 @@ typedef enum {
 
 /* ---- sampling: replaces include/pgm_random.h ------------------------------------------- */
 
-/* pgm_random_polyagamma (include/pgm_random.h:47-48): one draw, returned on the host
- * (synchronises `stream`).  Returns NaN if a CUDA call fails. */
+/* pgm_random_polyagamma (include/pgm_random.h:47-48): one draw, returned on the host.  One kernel launch
+ * that writes into mapped pinned memory of a slot the calling thread keeps per device (no allocation, no
+ * copy call after the first draw), then a stream synchronisation.  Returns NaN if a CUDA call fails. */
 double pgm_cuda_random_polyagamma(uint64_t seed, uint64_t offset, double h, double z, int method);
 
 /* pgm_random_polyagamma_fill (include/pgm_random.h:61-63): n iid draws of PG(h, z). */
@@ -87,16 +88,28 @@ int pgm_cuda_random_polyagamma_fill2_strided(uint64_t seed, uint64_t offset, con
                                              const int64_t* z_strides, double* d_out,
                                              uint64_t first_index, void* stream);
 
-/* Host-buffer form of fill2 (the reference's calling convention: all pointers are host
- * memory).  h_stride / z_stride are 1 (array of n) or 0 (scalar broadcast).  Copies are
- * chunked and overlapped with the kernels on internal streams of `device`; pinned (page-locked)
- * buffers give full PCIe speed.  Blocks until `out` is complete. */
+/* Host-buffer form of fill2 (the reference's calling convention: all pointers are host memory,
+ * include/pgm_random.h:72-74).  h_stride / z_stride are 1 (array of n) or 0 (scalar broadcast).  Copies are
+ * chunked and overlapped with the kernels on a ring of three internal streams of `device` (< 0: the current
+ * one); pinned (page-locked) buffers give full PCIe speed.  Blocks until `out` is complete; on failure it
+ * still does not return before every copy it queued has finished.  The ring's device staging (3 streams x 4
+ * operands x the chunk size, at most 64 MiB each, sized by the largest call so far) stays allocated until
+ * pgm_cuda_release_scratch.  Calls on different devices run concurrently; calls on one device take turns. */
 int pgm_cuda_random_polyagamma_fill2_host(uint64_t seed, uint64_t offset, const double* h,
                                           int h_stride, const double* z, int z_stride, int method,
                                           size_t n, double* out, uint64_t first_index, int device);
 
-/* Device time (CUDA events, first copy queued -> last copy done) of this process's most recent
- * pgm_cuda_random_polyagamma_fill2_host call, in milliseconds. */
+/* The same over SEVERAL devices from one host thread: the index range is cut into `ndevices` contiguous
+ * shards (shard i = [n i / ndevices, n (i + 1) / ndevices), on devices[i]), every shard runs through its own
+ * device's ring, and the chunks are queued round-robin so that all devices copy and compute at once.
+ * Elements keep their global Philox indices: the result is bit-identical for every ndevices. */
+int pgm_cuda_random_polyagamma_fill2_host_multi(uint64_t seed, uint64_t offset, const double* h, int h_stride,
+                                                const double* z, int z_stride, int method, size_t n,
+                                                double* out, uint64_t first_index, const int* devices,
+                                                int ndevices);
+
+/* Device time (CUDA events, first copy queued -> last copy done; the slowest device of a multi-device
+ * call) of the calling THREAD's most recent host-buffer fill, in milliseconds. */
 double pgm_cuda_last_host_fill_ms(void);
 
 /* Parameter check of polyagamma/_polyagamma.pyx:411-430 (any h <= 1e-4, or non-integer h when

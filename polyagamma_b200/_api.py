@@ -279,13 +279,17 @@ def _host_out_array(out):
 
 
 def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable_checks=False,
-                      random_state=None, device=None, ref_compat=False, first_index=0):
+                      random_state=None, device=None, ref_compat=False, first_index=0, devices=None):
     """Draw from PG(h, z).  Same contract as the reference's ``random_polyagamma``
     (``polyagamma/_polyagamma.pyx:22-256``); see the module docstring for the extensions.
 
     ``first_index`` is the global index of the first output element: a shard that passes the
     same ``random_state`` and its own ``first_index`` draws exactly what a single call over the
-    whole index range would draw for those elements (see ``polyagamma_b200.sharding``)."""
+    whole index range would draw for those elements (see ``polyagamma_b200.sharding``).
+
+    ``devices`` (host operands only): a sequence of CUDA device indices, or ``"all"``.  The index range is
+    cut into one contiguous shard per device and all devices copy and compute at once, from this one call
+    and host thread; the result is bit-identical to the single-device one."""
     mid = _method_id(method, ref_compat)
     fi = int(first_index)
     seed, offset = _resolve_random_state(random_state)
@@ -381,7 +385,7 @@ def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable
                              f"{harr.shape} {zarr.shape} {shape}")
     else:
         shape = _broadcast_shape(harr.shape, zarr.shape)
-    res = _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr, fi)
+    res = _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr, fi, devices)
     if arr is not None:
         if res is not arr:
             arr[...] = res
@@ -399,7 +403,7 @@ def _as_device_tensor_view(o, dev):
     return torch.from_dlpack(o)
 
 
-def _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr=None, first_index=0):
+def _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr=None, first_index=0, devices=None):
     """Host operands.  When h and z are each a scalar or already of the full output shape the
     pipelined host-buffer entry point is used (copies overlap the kernels); other broadcasts
     upload the un-broadcast operands and read the result back."""
@@ -415,6 +419,14 @@ def _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr=None, first_inde
     if linear(harr) and linear(zarr):
         direct = arr is not None and arr.dtype == np.float64 and arr.flags.c_contiguous and arr.flags.writeable
         res = arr if direct else np.empty(shape, dtype=np.float64)
+        if devices is not None:
+            devs = list(range(torch.cuda.device_count())) if devices == "all" else [int(d) for d in devices]
+            carr = (ctypes.c_int * len(devs))(*devs)
+            rc = _lib.lib().pgm_cuda_random_polyagamma_fill2_host_multi(
+                seed, offset, harr.ctypes.data, 0 if harr.size == 1 else 1, zarr.ctypes.data,
+                0 if zarr.size == 1 else 1, mid, n, res.ctypes.data, first_index, carr, len(devs))
+            _lib.check(rc, "pgm_cuda_random_polyagamma_fill2_host_multi")
+            return res
         rc = _lib.lib().pgm_cuda_random_polyagamma_fill2_host(
             seed, offset, harr.ctypes.data, 0 if harr.size == 1 else 1, zarr.ctypes.data,
             0 if zarr.size == 1 else 1, mid, n, res.ctypes.data, first_index, dev.index)
@@ -435,6 +447,15 @@ def _density(kind, x, h, z, return_log, device):
     """dispatch (polyagamma/_polyagamma.pyx:433-472)."""
     which = _WHICH[(kind, bool(return_log))]
     all_scalar = _is_number(x) and _is_number(h) and _is_number(z)
+    if all_scalar and device is None:
+        # the scalar fast path of dispatch() (polyagamma/_polyagamma.pyx:437-441): one point, one launch that
+        # reads and writes mapped pinned memory
+        _require_cuda()
+        buf = (ctypes.c_double * 4)(float(x), float(h), float(z), 0.0)
+        base = ctypes.addressof(buf)
+        rc = _lib.lib().pgm_cuda_polyagamma_density_host(which, base, 0, base + 8, 0, base + 16, 0, 1, base + 24, -1)
+        _lib.check(rc, "pgm_cuda_polyagamma_density_host")
+        return float(buf[3])
     on_device = any(_is_device_array(o) for o in (x, h, z)) or device is not None
     dev = _device_of(x, h, z, device=device)
     torch = _torch()

@@ -24,6 +24,7 @@ EXPORTS = (
     "pgm_cuda_random_polyagamma_fill2",
     "pgm_cuda_random_polyagamma_fill2_strided",
     "pgm_cuda_random_polyagamma_fill2_host",
+    "pgm_cuda_random_polyagamma_fill2_host_multi",
     "pgm_cuda_last_host_fill_ms",
     "pgm_cuda_any_invalid_h",
     "pgm_cuda_polyagamma_pdf",
@@ -75,6 +76,9 @@ def lib() -> ctypes.CDLL:
     L.pgm_cuda_random_polyagamma_fill2_strided.argtypes = [u64, u64, vp, vp, i, i, p64, p64, p64, vp, u64, vp]
     L.pgm_cuda_random_polyagamma_fill2_host.restype = i
     L.pgm_cuda_random_polyagamma_fill2_host.argtypes = [u64, u64, vp, i, vp, i, i, sz, vp, u64, i]
+    L.pgm_cuda_random_polyagamma_fill2_host_multi.restype = i
+    L.pgm_cuda_random_polyagamma_fill2_host_multi.argtypes = [u64, u64, vp, i, vp, i, i, sz, vp, u64,
+                                                              ctypes.POINTER(ctypes.c_int), i]
     L.pgm_cuda_last_host_fill_ms.restype = d
     L.pgm_cuda_last_host_fill_ms.argtypes = []
     L.pgm_cuda_any_invalid_h.restype = i

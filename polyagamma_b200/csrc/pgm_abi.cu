@@ -153,6 +153,7 @@ pgm_cuda_logistic_omega_step(uint64_t seed, uint64_t offset, const double* d_X, 
 int
 pgm_cuda_release_scratch(void)
 {
+    pgm::host_rings_release();
     return pgm::scratch_release();
 }
 
@@ -234,126 +235,6 @@ pgm_cuda_random_polyagamma_fill2_strided(uint64_t seed, uint64_t offset, const d
         }
     }
     return launch_fill(a, n, method, (cudaStream_t)stream);
-}
-
-double
-pgm_cuda_random_polyagamma(uint64_t seed, uint64_t offset, double h, double z, int method)
-{
-    double* d = nullptr;
-    double out = nan("");
-    if (cudaMalloc(&d, sizeof(double)) != cudaSuccess) return out;
-    int rc = pgm_cuda_random_polyagamma_fill(seed, offset, h, z, method, 1, d, 0, nullptr);
-    if (rc == 0 && cudaMemcpy(&out, d, sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) {
-        out = nan("");
-    }
-    cudaFree(d);
-    return out;
-}
-
-// ---- host-buffer fill2: chunked H2D -> kernels -> D2H on a ring of streams ---------------
-namespace {
-constexpr int kHostStreams = 3;
-constexpr size_t kHostChunk = size_t(1) << 23;  // elements per ring slot (64 MiB per buffer)
-
-struct HostRing {
-    bool ready = false;
-    cudaEvent_t ev_start, ev_end, ev_join[kHostStreams];
-    cudaStream_t streams[kHostStreams];
-    double* d_h[kHostStreams];
-    double* d_z[kHostStreams];
-    double* d_out[kHostStreams];
-};
-HostRing g_rings[64];
-std::mutex g_ring_mutex;
-double g_last_host_fill_ms = 0.0;
-
-int
-ring_init(HostRing& r)
-{
-    if (r.ready) return 0;
-    for (int i = 0; i < kHostStreams; ++i) {
-        cudaError_t e;
-        if ((e = cudaStreamCreateWithFlags(&r.streams[i], cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-        if ((e = cudaMalloc(&r.d_h[i], kHostChunk * sizeof(double))) != cudaSuccess) return (int)e;
-        if ((e = cudaMalloc(&r.d_z[i], kHostChunk * sizeof(double))) != cudaSuccess) return (int)e;
-        if ((e = cudaMalloc(&r.d_out[i], kHostChunk * sizeof(double))) != cudaSuccess) return (int)e;
-        cudaEventCreateWithFlags(&r.ev_join[i], cudaEventDisableTiming);
-    }
-    cudaEventCreate(&r.ev_start);
-    cudaEventCreate(&r.ev_end);
-    r.ready = true;
-    return 0;
-}
-}  // namespace
-
-int
-pgm_cuda_random_polyagamma_fill2_host(uint64_t seed, uint64_t offset, const double* h, int h_stride,
-                                      const double* z, int z_stride, int method, size_t n, double* out,
-                                      uint64_t first_index, int device)
-{
-    if (n == 0) return 0;
-    if (h == nullptr || z == nullptr || out == nullptr) return PGM_CUDA_EINVAL;
-    if ((h_stride != 0 && h_stride != 1) || (z_stride != 0 && z_stride != 1)) return PGM_CUDA_EINVAL;
-    DeviceGuard guard(device);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    std::lock_guard<std::mutex> lock(g_ring_mutex);
-    HostRing& r = g_rings[dev & 63];
-    int rc = ring_init(r);
-    if (rc != 0) return rc;
-
-    // device-side clock of the whole call: start on stream 0 before any copy is queued, end on
-    // stream 0 after it has joined the other ring streams
-    cudaEventRecord(r.ev_start, r.streams[0]);
-    for (int i = 1; i < kHostStreams; ++i) cudaStreamWaitEvent(r.streams[i], r.ev_start, 0);
-    size_t c = 0;
-    for (size_t off = 0; off < n; off += kHostChunk, ++c) {
-        const int slot = (int)(c % kHostStreams);
-        cudaStream_t s = r.streams[slot];
-        const size_t cn = (n - off) < kHostChunk ? (n - off) : kHostChunk;
-        FillArgs a = make_fill_args(seed, offset, r.d_out[slot], first_index + off);
-        cudaError_t e;
-        if (h_stride) {
-            if ((e = cudaMemcpyAsync(r.d_h[slot], h + off, cn * sizeof(double), cudaMemcpyHostToDevice, s)) !=
-                cudaSuccess)
-                return (int)e;
-            a.h = r.d_h[slot];
-        }
-        else {
-            a.h_scalar = h[0];
-        }
-        if (z_stride) {
-            if ((e = cudaMemcpyAsync(r.d_z[slot], z + off, cn * sizeof(double), cudaMemcpyHostToDevice, s)) !=
-                cudaSuccess)
-                return (int)e;
-            a.z = r.d_z[slot];
-        }
-        else {
-            a.z_scalar = z[0];
-        }
-        if ((rc = launch_fill(a, cn, method, s)) != 0) return rc;
-        if ((e = cudaMemcpyAsync(out + off, r.d_out[slot], cn * sizeof(double), cudaMemcpyDeviceToHost, s)) !=
-            cudaSuccess)
-            return (int)e;
-    }
-    for (int i = 1; i < kHostStreams; ++i) {
-        cudaEventRecord(r.ev_join[i], r.streams[i]);
-        cudaStreamWaitEvent(r.streams[0], r.ev_join[i], 0);
-    }
-    cudaEventRecord(r.ev_end, r.streams[0]);
-    for (int i = 0; i < kHostStreams; ++i) {
-        cudaError_t e = cudaStreamSynchronize(r.streams[i]);
-        if (e != cudaSuccess) return (int)e;
-    }
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, r.ev_start, r.ev_end) == cudaSuccess) g_last_host_fill_ms = ms;
-    return 0;
-}
-
-double
-pgm_cuda_last_host_fill_ms(void)
-{
-    return g_last_host_fill_ms;
 }
 
 int
@@ -463,59 +344,6 @@ pgm_cuda_polyagamma_density_strided(int which, const double* d_x, const double* 
         }
     }
     return launch_density(which, a, n, (cudaStream_t)stream);
-}
-
-int
-pgm_cuda_polyagamma_density_host(int which, const double* x, int x_stride, const double* h, int h_stride,
-                                 const double* z, int z_stride, size_t n, double* out, int device)
-{
-    if (which < 0 || which > 3) return PGM_CUDA_EINVAL;
-    if (n == 0) return 0;
-    if (x == nullptr || h == nullptr || z == nullptr || out == nullptr) return PGM_CUDA_EINVAL;
-    const int strides[3] = {x_stride, h_stride, z_stride};
-    for (int k = 0; k < 3; ++k)
-        if (strides[k] != 0 && strides[k] != 1) return PGM_CUDA_EINVAL;
-    DeviceGuard guard(device);
-    cudaStream_t s = nullptr;
-    cudaError_t e;
-    if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-    const size_t chunk = n < kHostChunk ? n : kHostChunk;
-    const double* src[3] = {x, h, z};
-    double* d[4] = {nullptr, nullptr, nullptr, nullptr};
-    int rc = 0;
-    for (int k = 0; k < 4 && rc == 0; ++k) {
-        const size_t len = (k < 3 && strides[k] == 0) ? 1 : chunk;
-        rc = pgm::scratch_alloc((void**)&d[k], len * sizeof(double), s);
-    }
-    for (int k = 0; k < 3 && rc == 0; ++k)
-        if (strides[k] == 0) rc = (int)cudaMemcpyAsync(d[k], src[k], sizeof(double), cudaMemcpyHostToDevice, s);
-    for (size_t off = 0; off < n && rc == 0; off += chunk) {
-        const size_t cn = (n - off) < chunk ? (n - off) : chunk;
-        for (int k = 0; k < 3 && rc == 0; ++k)
-            if (strides[k] == 1)
-                rc = (int)cudaMemcpyAsync(d[k], src[k] + off, cn * sizeof(double), cudaMemcpyHostToDevice, s);
-        if (rc != 0) break;
-        DensityArgs a;
-        memset(&a, 0, sizeof(a));
-        a.x = d[0];
-        a.h = d[1];
-        a.z = d[2];
-        a.out = d[3];
-        if (!(x_stride == 1 && h_stride == 1 && z_stride == 1)) {
-            a.bc.ndim = 1;
-            a.bc.shape[0] = (int64_t)cn;
-            a.bc.xs[0] = x_stride;
-            a.bc.hs[0] = h_stride;
-            a.bc.zs[0] = z_stride;
-        }
-        rc = launch_density(which, a, cn, s);
-        if (rc == 0) rc = (int)cudaMemcpyAsync(out + off, d[3], cn * sizeof(double), cudaMemcpyDeviceToHost, s);
-    }
-    for (int k = 0; k < 4; ++k)
-        if (d[k]) cudaFreeAsync(d[k], s);
-    e = cudaStreamSynchronize(s);
-    cudaStreamDestroy(s);
-    return rc != 0 ? rc : (int)e;
 }
 
 }  // extern "C"

@@ -54,6 +54,7 @@ int launch_logistic_omega_step(uint64_t seed, uint64_t offset, const double* d_X
 int device_init();                                          // per-device one-time setup (tables, scratch pool)
 int scratch_alloc(void** p, size_t bytes, cudaStream_t s);  // stream-ordered, from the library's private pool
 int scratch_release();
+void host_rings_release();  // pgm_host.cu: the staging buffers of the current device's host-buffer ring
 void evlog_report();  // PGM_CUDA_EVLOG diagnostic: which enqueued operations has the device completed?
 uint64_t launch_count();
 void count_launch(uint64_t n);

@@ -1124,7 +1124,7 @@ launch_dense(const DeviceInfo& d, const FillArgs& a, const Bucket& b, uint64_t c
     count_launch(1);
 }
 
-constexpr uint64_t kSmallMaxDefault = 1ull << 16;  // mixed-method fills break even near 1e5, single-method ones far later
+constexpr uint64_t kSmallMaxDefault = 1ull << 17;  // mixed-method fills break even near 1.4e5 (tools/perf_small_max.py), single-method ones far later
 
 static int
 env_int(const char* name, int lo, int hi, int fallback)

@@ -303,6 +303,61 @@ def test_host_buffer_path_equals_device_path(pg, torch):
     assert np.array_equal(host1, dev1.cpu().numpy())
 
 
+def test_host_multi_device_entry(pg, torch):
+    """pgm_cuda_random_polyagamma_fill2_host_multi: one host call, the index range cut over all visible devices
+    (with a single GPU: the degenerate partition, and argument checking).  Bit-identical to the single-device
+    result whatever the number of devices; small and ragged sizes; the staging is returned by release_scratch."""
+    from polyagamma_b200 import _lib
+
+    rng = np.random.default_rng(31)
+    ndev = torch.cuda.device_count()
+    for n in (1, 5, 100_003, (1 << 22) + 77):
+        h = rng.uniform(0.1, 120, n)
+        z = rng.uniform(-20, 20, n)
+        one = pg.random_polyagamma(h, z, random_state=(8, 1), disable_checks=True)
+        for devs in ([0], list(range(ndev)), "all"):
+            got = pg.random_polyagamma(h, z, random_state=(8, 1), disable_checks=True, devices=devs)
+            assert np.array_equal(got, one), (n, devs)
+        sc = pg.random_polyagamma(2.0, z, random_state=(8, 1), disable_checks=True, devices="all")
+        assert np.array_equal(sc, pg.random_polyagamma(2.0, z, random_state=(8, 1), disable_checks=True))
+    L = _lib.lib()
+    arr = (ctypes.c_int * 2)(0, 0)
+    h = np.ones(8)
+    out = np.empty(8)
+    assert L.pgm_cuda_random_polyagamma_fill2_host_multi(1, 0, h.ctypes.data, 1, h.ctypes.data, 1, _lib.HYBRID, 8,
+                                                         out.ctypes.data, 0, arr, 2) == _lib.EINVAL  # duplicate device
+    assert L.pgm_cuda_random_polyagamma_fill2_host_multi(1, 0, h.ctypes.data, 1, h.ctypes.data, 1, _lib.HYBRID, 8,
+                                                         out.ctypes.data, 0, arr, 0) == _lib.EINVAL
+    _lib.release_scratch()
+    again = pg.random_polyagamma(h, h, random_state=(8, 2), disable_checks=True)
+    assert np.all(np.isfinite(again))
+
+
+def test_bit_identical_across_devices(pg, torch):
+    """north_star: sampler outputs are bit-identical across 1/2/4/8-GPU partitionings for a given seed.  The
+    same global index range is drawn once on device 0 and shard-wise on all visible devices (every device draws
+    its contiguous shard with first_index); the concatenation must equal the single-device draw bit for bit.
+    With one visible GPU the shards all run on it (the partition logic is still exercised)."""
+    ndev = torch.cuda.device_count()
+    n = 1 << 22
+    g = torch.Generator(device="cuda:0")
+    g.manual_seed(99)
+    h = torch.rand(n, device="cuda:0", dtype=torch.float64, generator=g) * 199.9 + 0.1
+    h[::7] = torch.randint(1, 5, (h[::7].numel(),), device="cuda:0", generator=g).double()
+    z = torch.rand(n, device="cuda:0", dtype=torch.float64, generator=g) * 100 - 50
+    ref = pg.random_polyagamma(h, z, random_state=(123, 4), disable_checks=True)
+    for parts in sorted({1, 2, 3, max(ndev, 1), 8}):
+        pieces = []
+        for r in range(parts):
+            lo, hi = n * r // parts, n * (r + 1) // parts
+            dev = torch.device("cuda", r % ndev)
+            pieces.append(pg.random_polyagamma(h[lo:hi].to(dev), z[lo:hi].to(dev), random_state=(123, 4),
+                                               disable_checks=True, first_index=lo).to("cuda:0"))
+        assert torch.equal(torch.cat(pieces), ref), parts
+    for d in range(ndev):
+        torch.cuda.synchronize(d)
+
+
 def test_c_abi_direct_call(torch, oracle):
     """Straight through ctypes, no Python layer: device pointers in, device pointer out."""
     from polyagamma_b200 import _lib

@@ -35,20 +35,25 @@ if case.startswith("gibbs"):
     torch.cuda.synchronize()
     print("done", case, rows)
     sys.exit(0)
+m = int(round(n ** 0.5))
+gx = torch.linspace(1e-3, 12.5, m, device=dev, dtype=torch.float64)[:, None]
+gh = (0.5 + 24.5 * u1[:m])[None, :]
+gz = (zU[:m] / 5)[None, :]
 run = {
     "cfg1": lambda: pg.random_polyagamma(1.0, 0.0, size=n, device=dev, random_state=rs),
     "cfg2": lambda: pg.random_polyagamma(1.0, zN, **kw),
+    "cfg2_ones": lambda: pg.random_polyagamma(torch.ones_like(zN), zN, **kw),
     "cfg3_devroye": lambda: pg.random_polyagamma(torch.ones_like(zU), zU, method="devroye", **kw),
     "cfg3_alternate": lambda: pg.random_polyagamma(1 + 3 * u1, zU, method="alternate", **kw),
     "cfg3_saddle": lambda: pg.random_polyagamma(10 + 90 * u1, zU, method="saddle", **kw),
     "cfg3_gamma": lambda: pg.random_polyagamma(0.1 + 0.9 * u1[: n // 16], zU[: n // 16], method="gamma",
                                                out=out[: n // 16], random_state=rs, disable_checks=True),
     "cfg4": lambda: pg.random_polyagamma(0.1 + 199.9 * u1, zU, **kw),
-    "pdf": lambda: pg.polyagamma_pdf(u1 * 12.5 + 1e-3, 0.5 + 24.5 * u1.flip(0), zU / 5),
-    "logpdf": lambda: pg.polyagamma_pdf(u1 * 12.5 + 1e-3, 0.5 + 24.5 * u1.flip(0), zU / 5, return_log=True),
-    "cdf": lambda: pg.polyagamma_cdf(u1 * 12.5 + 1e-3, 0.5 + 24.5 * u1.flip(0), zU / 5),
-    "logcdf": lambda: pg.polyagamma_cdf((u1 * 12.5 + 1e-3)[: n // 8], (0.5 + 24.5 * u1.flip(0))[: n // 8],
-                                        (zU / 5)[: n // 8], return_log=True),
+    # cfg5a: x along rows, (h, z) along columns of a sqrt(n) x sqrt(n) broadcast grid
+    "pdf": lambda: pg.polyagamma_pdf(gx, gh, gz),
+    "logpdf": lambda: pg.polyagamma_pdf(gx, gh, gz, return_log=True),
+    "cdf": lambda: pg.polyagamma_cdf(gx, gh, gz),
+    "logcdf": lambda: pg.polyagamma_cdf(gx, gh, gz, return_log=True),
 }[case]
 for _ in range(reps):
     run()
