@@ -130,7 +130,12 @@ int pgm_cuda_polyagamma_logcdf(const double* d_x, const double* d_h, const doubl
                                double* d_out, void* stream);
 
 /* Broadcast form: which = 0 pdf, 1 cdf, 2 logpdf, 3 logcdf; out is C-contiguous with
- * `shape`; strides in doubles (0 = broadcast); shape/strides are HOST arrays. */
+ * `shape`; strides in doubles (0 = broadcast); shape/strides are HOST arrays.
+ * which = 4 .. 7 (not in the reference): the same four functions computed WITHOUT the
+ * alternating series' cancellation for h >= 8 -- by the trapezoid rule along the vertical line through the
+ * saddle point of the Laplace inversion integral (csrc/pgm_density.cu) -- where the reference's series loses
+ * sum|term| / |sum term| digits: all of them for h >~ 40 at small |z| (src/pgm_density.c:80-86,268-272).
+ * Agrees with the series in 300-digit arithmetic to 1e-12 (tests/golden/make_stable_golden.py). */
 int pgm_cuda_polyagamma_density_strided(int which, const double* d_x, const double* d_h,
                                         const double* d_z, int ndim, const int64_t* shape,
                                         const int64_t* x_strides, const int64_t* h_strides,

@@ -38,9 +38,14 @@ METHODS = {
     "saddle": _lib.SADDLE,
     "devroye": _lib.DEVROYE,
     "alternate": _lib.ALTERNATE,
+    # not in the reference: an EXACT sampler for every h >= 1 -- the alternate method's pieces,
+    # PG(h, z) = sum of PG(b_i, z) with b_i <= 4 (src/pgm_alternate.c:294-323), with the mathematically consistent
+    # envelope whatever ref_compat says; the hybrid rule's saddle / normal methods are approximations
+    "exact": _lib.EXACT,
 }
 ZERO = 1e-04  # polyagamma/_polyagamma.pyx:399
 PARAM_CHECK_ERROR_MSG = "Values of `h` must be positive, and also integer if `method` is devroye."
+EXACT_ERROR_MSG = "`method='exact'` needs h >= 1 (the alternate sampler's pieces are exact from h = 1 on)."
 
 _MASK64 = (1 << 64) - 1
 
@@ -291,6 +296,9 @@ def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable
     cut into one contiguous shard per device and all devices copy and compute at once, from this one call
     and host thread; the result is bit-identical to the single-device one."""
     mid = _method_id(method, ref_compat)
+    exact = (mid & 0xff) == _lib.EXACT
+    if exact:
+        mid = _lib.ALTERNATE  # (default envelope: ref_compat is ignored)
     fi = int(first_index)
     seed, offset = _resolve_random_state(random_state)
     has_size = size is not None
@@ -301,6 +309,8 @@ def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable
         ch, cz = float(h), float(z)
         if not disable_checks and (ch <= ZERO or ((mid & 0xff) == _lib.DEVROYE and ch != np.floor(ch))):
             raise ValueError(PARAM_CHECK_ERROR_MSG)
+        if exact and not ch >= 1.0:
+            raise ValueError(EXACT_ERROR_MSG)
         if has_size:
             shape = _shape_from_size(size)
             n = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
@@ -342,6 +352,8 @@ def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable
         zt = _as_device_tensor(z, dev)
         if not disable_checks and _check_h_device(ht, mid, dev):
             raise ValueError(PARAM_CHECK_ERROR_MSG)
+        if exact and not disable_checks and bool((ht < 1.0).any()):
+            raise ValueError(EXACT_ERROR_MSG)
         if has_size:
             shape = _broadcast_shape(tuple(ht.shape), tuple(zt.shape), _shape_from_size(size))
             if shape != _shape_from_size(size):
@@ -370,6 +382,8 @@ def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable
     if not disable_checks and _check_h_host(harr, mid):
         raise ValueError(PARAM_CHECK_ERROR_MSG)
     zarr = np.asarray(z, dtype=np.float64, order="C")
+    if exact and not disable_checks and bool(np.any(harr < 1.0)):
+        raise ValueError(EXACT_ERROR_MSG)
     arr = None
     if has_size:
         want = _shape_from_size(size)
@@ -443,9 +457,9 @@ def _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr=None, first_inde
 _WHICH = {("pdf", False): 0, ("cdf", False): 1, ("pdf", True): 2, ("cdf", True): 3}
 
 
-def _density(kind, x, h, z, return_log, device):
+def _density(kind, x, h, z, return_log, device, stable=False):
     """dispatch (polyagamma/_polyagamma.pyx:433-472)."""
-    which = _WHICH[(kind, bool(return_log))]
+    which = _WHICH[(kind, bool(return_log))] + (4 if stable else 0)
     all_scalar = _is_number(x) and _is_number(h) and _is_number(z)
     if all_scalar and device is None:
         # the scalar fast path of dispatch() (polyagamma/_polyagamma.pyx:437-441): one point, one launch that
@@ -480,11 +494,16 @@ def _density(kind, x, h, z, return_log, device):
     return out.cpu().numpy()
 
 
-def polyagamma_pdf(x, h=1.0, z=0.0, return_log=False, *, device=None):
-    """Density of PG(h, z) at x (``polyagamma/_polyagamma.pyx:259-324``)."""
-    return _density("pdf", x, h, z, return_log, device)
+def polyagamma_pdf(x, h=1.0, z=0.0, return_log=False, *, device=None, stable=False):
+    """Density of PG(h, z) at x (``polyagamma/_polyagamma.pyx:259-324``).
+
+    ``stable=True`` (not in the reference): for h >= 8 the value comes from a saddle-point contour integral
+    instead of the reference's alternating series, which loses every digit for h >~ 40 at small |z|
+    (SURVEY 8-DEFECTS g).  The default reproduces the reference's numbers, cancellation included."""
+    return _density("pdf", x, h, z, return_log, device, stable)
 
 
-def polyagamma_cdf(x, h=1.0, z=0.0, return_log=False, *, device=None):
-    """Distribution function of PG(h, z) at x (``polyagamma/_polyagamma.pyx:327-384``)."""
-    return _density("cdf", x, h, z, return_log, device)
+def polyagamma_cdf(x, h=1.0, z=0.0, return_log=False, *, device=None, stable=False):
+    """Distribution function of PG(h, z) at x (``polyagamma/_polyagamma.pyx:327-384``); ``stable`` as in
+    :func:`polyagamma_pdf`."""
+    return _density("cdf", x, h, z, return_log, device, stable)

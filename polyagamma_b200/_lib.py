@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpgm_cuda.so")
 # include/pgm_cuda.h: pgm_cuda_sampler_t (same values as the reference's sampler_t,
 # include/pgm_random.h:13)
 GAMMA, DEVROYE, ALTERNATE, SADDLE, HYBRID = range(5)
+EXACT = 6  # Python layer only: drawn as ALTERNATE with the consistent envelope, for h >= 1
 REF_COMPAT = 0x100
 EINVAL = -1
 

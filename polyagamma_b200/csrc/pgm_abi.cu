@@ -308,7 +308,7 @@ pgm_cuda_polyagamma_density_strided(int which, const double* d_x, const double* 
                                     const int64_t* shape, const int64_t* x_strides, const int64_t* h_strides,
                                     const int64_t* z_strides, double* d_out, void* stream)
 {
-    if (ndim < 0 || ndim > PGM_CUDA_MAX_NDIM || which < 0 || which > 3) return PGM_CUDA_EINVAL;
+    if (ndim < 0 || ndim > PGM_CUDA_MAX_NDIM || which < 0 || which > 7) return PGM_CUDA_EINVAL;
     uint64_t n = 1;
     for (int d = 0; d < ndim; ++d) {
         if (shape[d] < 0) return PGM_CUDA_EINVAL;

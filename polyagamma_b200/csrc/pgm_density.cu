@@ -272,6 +272,183 @@ pg_logcdf(double x, double h, double z)
     return c + (first + log(sum));
 }
 
+// ---------------------------------------------------------------------------------------
+// Cancellation-free densities for large h: which = 4..7
+// ---------------------------------------------------------------------------------------
+// The alternating series above (the reference's, src/pgm_density.c:80-86,268-272) loses cond = sum|term| /
+// |sum term| digits: everything for h >~ 40 at small |z| (8-DEFECTS g).  The opt-in "stable" forms invert the
+// Laplace transform instead,
+//     E exp(-t X) = [cosh(z/2) / cosh r(t)]^h,   r(t) = sqrt(z^2/4 + t/2),    X ~ PG(h, z),
+//     pdf(x) = 1/(2 pi i) int exp(psi(t)) dt,       psi(t) = t x + h (log cosh(z/2) - log cosh r(t)),
+//     cdf(x) = 1/(2 pi i) int exp(psi(t)) / t dt    (Re t = c > 0;  c < 0 gives cdf(x) - 1),
+// along the vertical line through the real saddle point t0 of psi (psi'(t0) = 0 is the equation
+// K'(u) = 4x/h of the saddle-point sampler, t0 = -4u - z^2/2): there the integrand is largest at y = 0 and falls
+// off like a Gaussian of width 1/sigma, sigma^2 = psi''(t0) = h K''(u) / 16, so nothing cancels, and the
+// trapezoid rule in y converges geometrically (analytic integrand).  Step 0.2 / sigma: the nearest singularity
+// of the cdf integrand (the pole at t = 0) is kept at least 1.1 / sigma = 5.5 steps away by moving the line to
+// c = +1.1 / sigma when |t0| is smaller than that (at most a factor e^{2.4} off the saddle), which bounds the
+// quadrature error by e^{-2 pi 5.5} ~ 1e-15.  The sum stops when the integrand has fallen below 1e-18 of it.
+// Checked against the same series in 300-digit arithmetic (tests/golden/make_stable_golden.py): <= 1e-12
+// relative for h >= 8 wherever the result is above 1e-290.  Below h = 8 the series itself is well conditioned
+// and is used (its answers and these agree to 1e-10 on the overlap, tests/test_gpu_parity.py).
+struct cplx {
+    double re, im;
+};
+// K'(u) and K''(u) of the cumulant of J*(1, 0): tanh(s)/s with s = sqrt(-2u) for u < 0, tan(s)/s with
+// s = sqrt(2u) for u > 0 (src/pgm_saddle.c:100-107, exact functions), K'' = K'^2 + (1 - K') / (2u)
+__device__ __forceinline__ void
+stable_kprime(double u, double& f, double& fp)
+{
+    const double s2 = 2.0 * u;
+    if (fabs(s2) < 1e-4) {
+        const double g = 1.0 / 3.0 + s2 * (2.0 / 15.0 + s2 * (17.0 / 315.0));
+        f = 1.0 + s2 * g;
+        fp = f * f - g;
+        return;
+    }
+    const double s = ::sqrt(fabs(s2));
+    f = (s2 > 0.0 ? tan(s) : tanh(s)) / s;
+    fp = f * f + (1.0 - f) / s2;
+}
+// root u of K'(u) = xp (xp > 0): Newton's iteration kept inside a bracket
+__device__ double
+stable_saddle(double xp, double& fp)
+{
+    const double kUMax = 1.2337005501361697;  // pi^2 / 8: the pole of tan
+    double s_lo = 1.0 / xp + 1.0;
+    double lo = -0.5 * s_lo * s_lo, hi = kUMax;  // K'(lo) < xp < K'(hi -> pole)
+    double u = (xp < 1.0) ? -0.5 / (xp * xp) : (xp < 1.5 ? 0.3 : kUMax * (1.0 - 0.4 / xp));
+    if (!(u > lo)) u = 0.5 * (lo + hi);
+    double f = 1.0;
+    for (int it = 0; it < 80; ++it) {
+        stable_kprime(u, f, fp);
+        const double g = f - xp;
+        if (fabs(g) <= 1e-14 * xp) break;
+        if (g > 0.0) hi = u;
+        else lo = u;
+        double un = u - g / fp;
+        if (!(un > lo && un < hi)) un = 0.5 * (lo + hi);
+        if (un == u) break;
+        u = un;
+    }
+    stable_kprime(u, f, fp);
+    return u;
+}
+__device__ __forceinline__ cplx
+csqrt_pos(cplx a)  // principal square root (Re >= 0)
+{
+    const double m = ::sqrt(a.re * a.re + a.im * a.im);
+    cplx r;
+    if (a.re >= 0.0) {
+        r.re = ::sqrt(0.5 * (m + a.re));
+        r.im = (r.re > 0.0) ? 0.5 * a.im / r.re : 0.0;
+    }
+    else {
+        const double q = ::sqrt(0.5 * (m - a.re));
+        r.re = 0.5 * fabs(a.im) / q;
+        r.im = (a.im >= 0.0) ? q : -q;
+    }
+    return r;
+}
+// log cosh r for Re r >= 0: r - log 2 + log(1 + e^{-2r})
+__device__ __forceinline__ cplx
+clogcosh(cplx r)
+{
+    const double e = ::exp(-2.0 * r.re);
+    double sn, cs;
+    sincos(-2.0 * r.im, &sn, &cs);
+    const double ar = e * cs, ai = e * sn;  // a = e^{-2r}, |a| <= 1
+    cplx v;
+    v.re = r.re - kLog2 + 0.5 * log1p(2.0 * ar + ar * ar + ai * ai);
+    v.im = r.im + atan2(ai, 1.0 + ar);
+    return v;
+}
+
+// mode 0: log pdf; 1: log of cdf-or-survival, `upper` says which: upper = false -> log cdf(x),
+// upper = true -> log(1 - cdf(x)) (taken whenever the saddle lies left of the pole: x well above the mean)
+__device__ double
+pg_contour(int mode, double x, double h, double z, bool& upper)
+{
+    upper = false;
+    const double az = fabs(z), hz = 0.5 * az;
+    const double lcz = hz - kLog2 + log1p(::exp(-2.0 * hz));  // log cosh(z/2)
+    // real saddle point: K'(u) = 4x/h
+    const double xp = 4.0 * x / h;
+    double fp;
+    const double u = stable_saddle(xp, fp);
+    const double t0 = -4.0 * u - 0.5 * az * az;
+    const double sigma = ::sqrt(0.0625 * h * fp);
+    const double dy = 0.2 / sigma;
+    double c = t0;
+    if (mode == 1) {
+        const double cmin = 1.1 / sigma;
+        if (fabs(t0) < cmin) c = cmin;
+        upper = c < 0.0;
+    }
+    // psi at the real point c (the integrand is normalised by it)
+    double psi0;
+    {
+        const double w = 0.25 * az * az + 0.5 * c;  // r^2, real; negative: r = i rho, cosh r = cos rho
+        const double lcr = (w >= 0.0) ? (::sqrt(w) - kLog2 + log1p(::exp(-2.0 * ::sqrt(w)))) : ::log(cos(::sqrt(-w)));
+        psi0 = c * x + h * (lcz - lcr);
+    }
+    double sum = (mode == 0) ? 0.5 : 0.5 / c;  // the y = 0 term, weight 1/2
+    int small = 0;
+    for (int k = 1; k < 4096; ++k) {
+        const double y = k * dy;
+        cplx r2{0.25 * az * az + 0.5 * c, 0.5 * y};
+        const cplx lcr = clogcosh(csqrt_pos(r2));
+        const double pre = c * x + h * (lcz - lcr.re) - psi0, pim = y * x - h * lcr.im;
+        const double mag = ::exp(pre);
+        double sn, cs;
+        sincos(pim, &sn, &cs);
+        double term;
+        if (mode == 0) {
+            term = mag * cs;
+        }
+        else {  // Re(e^{i pim} / (c + i y)) = (c cos + y sin) / (c^2 + y^2)
+            term = mag * (c * cs + y * sn) / (c * c + y * y);
+        }
+        sum += term;
+        const double scale = (mode == 0) ? 1.0 : 1.0 / hypot(c, y);
+        if (mag * scale < 1e-18 * fabs(sum)) {
+            if (++small >= 3) break;
+        }
+        else {
+            small = 0;
+        }
+    }
+    // pdf = e^{psi0} dy / pi * sum;  cdf (c > 0) or cdf - 1 (c < 0) = the same with 1/t under the integral
+    const double lg = psi0 + ::log(dy * 0.3183098861837907 * fabs(sum));
+    if (mode == 1 && upper && !(sum < 0.0)) return -INFINITY;  // (cdf - 1 must be negative: rounding at cdf = 1)
+    return lg;
+}
+
+constexpr double kStableMinH = 8.0;  // below: the series is well conditioned (and the integrand decays slowly)
+
+__device__ double
+pg_pdf_stable(double x, double h, double z, bool want_log)
+{
+    if (!(h >= kStableMinH)) return want_log ? pg_logpdf(x, h, z) : pg_pdf(x, h, z);
+    if (!(x > 0.0) || isinf(x)) return want_log ? -INFINITY : 0.0;
+    bool upper;
+    const double l = pg_contour(0, x, h, z, upper);
+    return want_log ? l : ::exp(l);
+}
+
+__device__ double
+pg_cdf_stable(double x, double h, double z, bool want_log)
+{
+    if (!(h >= kStableMinH)) return want_log ? pg_logcdf(x, h, z) : pg_cdf(x, h, z);
+    if (!(x > 0.0)) return want_log ? -INFINITY : 0.0;
+    if (isinf(x)) return want_log ? 0.0 : 1.0;
+    bool upper;
+    const double l = pg_contour(1, x, h, z, upper);
+    if (!upper) return want_log ? fmin(l, 0.0) : fmin(::exp(l), 1.0);
+    const double sf = ::exp(l);  // 1 - cdf
+    return want_log ? log1p(-sf) : 1.0 - sf;
+}
+
 template <int WHICH>
 __global__ void __launch_bounds__(256)
 density_kernel(DensityArgs a, uint64_t n)
@@ -295,7 +472,11 @@ density_kernel(DensityArgs a, uint64_t n)
         if (WHICH == 0) v = pg_pdf(x, h, z);
         else if (WHICH == 1) v = pg_cdf(x, h, z);
         else if (WHICH == 2) v = pg_logpdf(x, h, z);
-        else v = pg_logcdf(x, h, z);
+        else if (WHICH == 3) v = pg_logcdf(x, h, z);
+        else if (WHICH == 4) v = pg_pdf_stable(x, h, z, false);
+        else if (WHICH == 5) v = pg_cdf_stable(x, h, z, false);
+        else if (WHICH == 6) v = pg_pdf_stable(x, h, z, true);
+        else v = pg_cdf_stable(x, h, z, true);
         a.out[i] = v;
     }
 }
@@ -304,7 +485,7 @@ int
 launch_density(int which, DensityArgs a, uint64_t n, cudaStream_t s)
 {
     if (n == 0) return 0;
-    if (which < 0 || which > 3) return -1;
+    if (which < 0 || which > 7) return -1;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -316,7 +497,11 @@ launch_density(int which, DensityArgs a, uint64_t n, cudaStream_t s)
         case 0: density_kernel<0><<<grid, 256, 0, s>>>(a, n); break;
         case 1: density_kernel<1><<<grid, 256, 0, s>>>(a, n); break;
         case 2: density_kernel<2><<<grid, 256, 0, s>>>(a, n); break;
-        default: density_kernel<3><<<grid, 256, 0, s>>>(a, n); break;
+        case 3: density_kernel<3><<<grid, 256, 0, s>>>(a, n); break;
+        case 4: density_kernel<4><<<grid, 256, 0, s>>>(a, n); break;
+        case 5: density_kernel<5><<<grid, 256, 0, s>>>(a, n); break;
+        case 6: density_kernel<6><<<grid, 256, 0, s>>>(a, n); break;
+        default: density_kernel<7><<<grid, 256, 0, s>>>(a, n); break;
     }
     count_launch(1);
     return (int)cudaGetLastError();

@@ -372,7 +372,7 @@ int
 pgm_cuda_polyagamma_density_host(int which, const double* x, int x_stride, const double* h, int h_stride,
                                  const double* z, int z_stride, size_t n, double* out, int device)
 {
-    if (which < 0 || which > 3) return PGM_CUDA_EINVAL;
+    if (which < 0 || which > 7) return PGM_CUDA_EINVAL;
     if (n == 0) return 0;
     if (x == nullptr || h == nullptr || z == nullptr || out == nullptr) return PGM_CUDA_EINVAL;
     const int strides[3] = {x_stride, h_stride, z_stride};

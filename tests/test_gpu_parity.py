@@ -662,6 +662,94 @@ def test_density_vs_compiled_reference(pg, ref, oracle, name, kind, log):
     assert np.all(err[well] <= tol[well])
 
 
+def test_stable_densities_against_300_digit_series(pg, torch):
+    """polyagamma_pdf / polyagamma_cdf(..., stable=True) against the reference's alternating series
+    evaluated in 300-digit arithmetic (tests/golden/stable_density_golden.npz), h from 8 to 200, z from 0 to 20,
+    x = mean + k sd -- including the cells where the default (reference-exact) series has no correct digit.
+    Tolerance: 1e-10 relative (the north_star tolerance for pdf / cdf) on the value, on 1 - cdf, and on the logs."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stable_density_golden.npz"))
+    x, h, z = (torch.from_numpy(g[k]).cuda() for k in ("x", "h", "z"))
+    pdf = pg.polyagamma_pdf(x, h, z, stable=True).cpu().numpy()
+    cdf = pg.polyagamma_cdf(x, h, z, stable=True).cpu().numpy()
+    lpdf = pg.polyagamma_pdf(x, h, z, return_log=True, stable=True).cpu().numpy()
+    lcdf = pg.polyagamma_cdf(x, h, z, return_log=True, stable=True).cpu().numpy()
+    ok = g["pdf"] > 1e-290
+    assert np.max(np.abs(pdf[ok] - g["pdf"][ok]) / g["pdf"][ok]) < 1e-10
+    assert np.max(np.abs(lpdf[ok] - np.log(g["pdf"][ok]))) < 1e-10
+    ok = g["cdf"] > 1e-290
+    assert np.max(np.abs(cdf[ok] - g["cdf"][ok]) / g["cdf"][ok]) < 1e-10
+    assert np.max(np.abs(lcdf[ok] - np.log(g["cdf"][ok]))) < 1e-10
+    ok = g["sf"] > 1e-9  # (1 - cdf is formed from a double: absolute 1e-16)
+    assert np.max(np.abs((1 - cdf[ok]) - g["sf"][ok]) / g["sf"][ok]) < 1e-6
+    # the default path on the same points: fine at h = 8, useless at h = 200 and small z (why `stable` exists)
+    plain = pg.polyagamma_pdf(x, h, z).cpu().numpy()
+    small = (g["h"] == 8) & (g["pdf"] > 1e-290)
+    assert np.max(np.abs(plain[small] - g["pdf"][small]) / g["pdf"][small]) < 1e-9
+    big = (g["h"] == 200) & (g["z"] <= 1)
+    assert np.median(np.abs(plain[big] - g["pdf"][big]) / g["pdf"][big]) > 1.0
+
+
+def test_stable_densities_agree_with_series_where_it_is_well_conditioned(pg, torch, oracle):
+    """On a fresh grid with h in [8, 25] (contour integral) and h in [0.5, 8) (the series, unchanged): stable = True
+    and the default agree to 1e-10 wherever the series' condition number is below 100; edge values; evenness in z;
+    monotone cdf; pdf = d cdf / dx to quadrature accuracy at h = 150, z = 0.3, where the default is noise."""
+    rng = np.random.default_rng(81)
+    n = 20000
+    h = rng.uniform(0.5, 25.0, n)
+    z = rng.uniform(-12.0, 12.0, n)
+    mean = np.where(np.abs(z) > 1e-6, h * np.tanh(z / 2) / (2 * z), h / 4)
+    x = mean * rng.uniform(0.3, 2.5, n)
+    for kind, f in (("pdf", pg.polyagamma_pdf), ("cdf", pg.polyagamma_cdf)):
+        want, cond = oracle.density(kind, x, h, z, return_cond=True)
+        got = f(x, h, z, stable=True)
+        ok = np.isfinite(want) & (cond < 100) & (want > 1e-280)
+        assert ok.sum() > n // 3
+        assert np.max(np.abs(got[ok] - want[ok]) / want[ok]) < 1e-10, kind
+        lg = f(x, h, z, return_log=True, stable=True)
+        assert np.max(np.abs(lg[ok] - np.log(want[ok]))) < 1e-9, kind
+    assert pg.polyagamma_pdf(0.0, 50.0, 1.0, stable=True) == 0.0 and pg.polyagamma_cdf(-1.0, 50.0, 1.0, stable=True) == 0.0
+    assert pg.polyagamma_cdf(np.inf, 50.0, 1.0, stable=True) == 1.0
+    assert pg.polyagamma_cdf(np.inf, 50.0, 1.0, return_log=True, stable=True) == 0.0
+    xs = torch.linspace(20.0, 55.0, 200001, device="cuda", dtype=torch.float64)
+    F = pg.polyagamma_cdf(xs, 150.0, 0.3, stable=True)
+    f = pg.polyagamma_pdf(xs, 150.0, 0.3, stable=True)
+    assert torch.equal(F, pg.polyagamma_cdf(xs, 150.0, -0.3, stable=True))
+    assert bool((F[1:] >= F[:-1] - 1e-15).all()) and float(F[0]) < 1e-6 and float(F[-1]) > 1 - 1e-6
+    dx = float(xs[1] - xs[0])
+    simpson = (f[:-2:2] + 4 * f[1:-1:2] + f[2::2]).cumsum(0) * dx / 3
+    assert float((F[2::2] - F[0] - simpson).abs().max()) < 1e-10  # (1e5 panels: the cumulative sum rounds at 1e-11)
+
+
+@pytest.mark.parametrize("h,z,n", [(6.5, 0.7, 4_000_000), (30.0, 2.0, 2_000_000), (75.0, 0.5, 1_000_000), (200.0, 1.0, 400_000),
+                                   (120.0, 15.0, 500_000)])
+def test_exact_sampler_large_h(pg, torch, h, z, n):
+    """method="exact" (PG(h, z) as a sum of alternate pieces, exact for every h >= 1) against the
+    cancellation-free cdf -- KS and Anderson-Darling -- and the exact moments, in cells where the hybrid rule would
+    use the saddle-point or normal APPROXIMATIONS and the reference's own cdf has no correct digit."""
+    x = pg.random_polyagamma(float(h), float(z), size=n, method="exact", random_state=(77, 1), device="cuda")
+    mean, var = pg_moments(h, z)
+    xm = float(x.mean())
+    xc = x - xm
+    v = float((xc * xc).mean())
+    m4 = float((xc**4).mean())
+    assert abs((xm - mean) / np.sqrt(var / n)) < 4 and abs((v - var) / np.sqrt((m4 - var * var) / n)) < 4
+    xs, _ = torch.sort(x)
+    F = pg.polyagamma_cdf(xs, float(h), float(z), stable=True)
+    i = torch.arange(1, n + 1, device="cuda", dtype=torch.float64)
+    d = max(float((i / n - F).max()), float((F - (i - 1) / n).max()))
+    assert d * np.sqrt(n) < 1.95, d * np.sqrt(n)
+    Fc = F.clamp(1e-300, 1.0 - 1e-16)
+    a2 = -n - float(((2 * i - 1) * (torch.log(Fc) + torch.log1p(-Fc.flip(0)))).sum()) / n
+    assert a2 < 6.0, a2
+    with pytest.raises(ValueError):
+        pg.random_polyagamma(0.5, 1.0, size=4, method="exact")
+    # the hybrid rule's draw in the same cell is an approximation: distinguishable from the exact law at this n
+    # only for the normal approximation at moderate h (skewness); here it just has to run
+    assert pg.random_polyagamma(float(h), float(z), size=8, random_state=(1, 1)).shape == (8,)
+
+
 # ------------------------------------------------------------------------------------------
 # statistics at 1e7 draws per cell (north_star: mean/var within 4 SE, KS vs cdf, two-sample KS)
 # ------------------------------------------------------------------------------------------
@@ -699,12 +787,18 @@ def test_gamma_truncated_moments(pg, h, z):
     assert abs(zm) < 4 and abs(zv) < 4, (zm, zv)
 
 
-@pytest.mark.parametrize("method,h,z", [("devroye", 1, 0), ("devroye", 2, -5), ("alternate", 1.5, 0),
-                                        ("alternate", 2.5, 0), ("alternate", 3.5, 1), ("alternate", 4, 3),
-                                        (None, 3, 2.5), (None, 1, 1)])
-def test_ks_against_cdf_1e7(pg, torch, method, h, z):
-    """KS of 1e7 draws against polyagamma_cdf (the CUDA cdf, itself parity-checked above against
-    the reference's) for the exact samplers, in cells where the cdf series is well conditioned."""
+CDF_CELLS = [("devroye", 1, 0), ("devroye", 2, -5), ("devroye", 1, 6), ("devroye", 3, 20), ("alternate", 1.5, 0),
+             ("alternate", 2.5, 0), ("alternate", 3.5, 1), ("alternate", 4, 3), ("alternate", 6.5, 10),
+             (None, 3, 2.5), (None, 1, 1), ("exact", 12, 6), ("exact", 30, 8), ("exact", 7.5, 2)]
+
+
+@pytest.mark.parametrize("method,h,z", CDF_CELLS)
+def test_ks_and_anderson_darling_against_cdf_1e7(pg, torch, method, h, z):
+    """Kolmogorov-Smirnov AND Anderson-Darling of 1e7 draws against polyagamma_cdf (the CUDA cdf, itself
+    parity-checked above against the reference's) for the exact samplers, in cells where the cdf series is
+    well conditioned.  north_star: "KS/AD against the reference polyagamma_cdf".
+    KS: sqrt(n) D < 1.95 (p ~ 1e-3).  AD: A^2 = -n - 1/n sum (2i - 1)(ln F_i + ln(1 - F_{n+1-i})) < 6.0 (the
+    asymptotic 0.1 % point); it weighs the tails, where KS is blind."""
     x = pg.random_polyagamma(float(h), float(z), size=N_STAT, method=method, random_state=(2024, 2), device="cuda")
     xs, _ = torch.sort(x)
     F = pg.polyagamma_cdf(xs, float(h), float(z))
@@ -712,6 +806,9 @@ def test_ks_against_cdf_1e7(pg, torch, method, h, z):
     i = torch.arange(1, n + 1, device="cuda", dtype=torch.float64)
     d = max(float((i / n - F).max()), float((F - (i - 1) / n).max()))
     assert d * np.sqrt(n) < 1.95, d * np.sqrt(n)  # p ~ 1e-3
+    Fc = F.clamp(1e-300, 1.0 - 1e-16)
+    a2 = -n - float(((2 * i - 1) * (torch.log(Fc) + torch.log1p(-Fc.flip(0)))).sum()) / n
+    assert a2 < 6.0, a2
 
 
 def test_two_sample_vs_golden_reference_quantiles(pg, sampler_golden):
@@ -730,21 +827,103 @@ def test_two_sample_vs_golden_reference_quantiles(pg, sampler_golden):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("method,h,z,compat", [("devroye", 1, 0, False), ("devroye", 3, 2, False),
-                                               ("alternate", 2.5, 0, True), ("alternate", 3.5, 1, True),
-                                               ("alternate", 0.5, 0, False), ("alternate", 2.7, 30, False),
-                                               ("saddle", 4.5, 0, True), ("saddle", 10, 2, False),
-                                               ("saddle", 30, 5, False), (None, 60, 5, False),
-                                               (None, 2.5, 3, True)])
+# every row of SURVEY.md's parity matrix (8-DEFECTS): (method, h, z, mode the register says must agree)
+LIVE_CELLS = [("devroye", 1, 0, False), ("devroye", 3, 2, False), ("devroye", 1, 6, False), ("devroye", 2, 20, False),
+              ("devroye", 4, -45, False),                                            # Michael-Schucany-Haas bucket
+              ("alternate", 2.5, 0, True), ("alternate", 3.5, 1, True), ("alternate", 0.5, 0, False),
+              ("alternate", 2.7, 30, False), ("alternate", 9.5, 6, True),
+              (None, 0.5, 0, False), (None, 0.3, 2, False),                          # h < 1 through the hybrid rule
+              ("saddle", 4.5, 0, True), ("saddle", 10, 2, False), ("saddle", 30, 5, False),
+              ("saddle", 8, 0, False), ("saddle", 10, 1, False), ("saddle", 12, 3, False),  # 8 <= h < 15, small z
+              ("saddle", 40, 20, False),
+              (None, 60, 5, False), (None, 51, 0, False), (None, 120, 20, False), (None, 200, 30, False),  # normal, |z| < 36
+              (None, 2.5, 3, True),
+              ("gamma", 1, 0, False), ("gamma", 0.5, 2, False), ("gamma", 2.5, 10, False)]
+
+
+@pytest.mark.parametrize("method,h,z,compat", LIVE_CELLS)
 def test_two_sample_ks_vs_live_reference_1e7(pg, ref, method, h, z, compat):
     """Two-sample KS at 1e7 draws against the compiled reference drawing with numpy PCG64, in
     the mode the defect register says must agree (default where the reference is clean,
     ref_compat where its envelope constants bias it)."""
     from scipy import stats
 
-    x = pg.random_polyagamma(float(h), float(z), size=N_STAT, method=method, random_state=(31337, 0),
+    n = N_STAT if method != "gamma" else 2_000_000  # (the reference's gamma sampler draws 5e5 samples/s)
+    x = pg.random_polyagamma(float(h), float(z), size=n, method=method, random_state=(31337, 0),
                              ref_compat=compat)
-    y = ref.random_polyagamma(h, z, size=N_STAT, method=method,
+    y = ref.random_polyagamma(h, z, size=n, method=method,
                               random_state=np.random.Generator(np.random.PCG64(99)))
     r = stats.ks_2samp(x, y)
-    assert r.statistic * np.sqrt(N_STAT / 2) < 1.95, r
+    assert r.statistic * np.sqrt(n / 2) < 1.95, r
+
+
+def _standardised(x, mean, var, mask=None):
+    """z-scores of the mean and of the mean square of (x - E) / sd over the masked elements."""
+    r = (x - mean) / var.sqrt()
+    if mask is not None:
+        r = r[mask]
+    n = r.numel()
+    m1, m2 = float(r.mean()), float((r * r).mean())
+    m4 = float((r**4).mean())
+    return n, m1 * np.sqrt(n), (m2 - 1.0) * np.sqrt(n / max(m4 - 1.0, 1e-12))
+
+
+def _pg_moments_t(torch, h, z):
+    a = z.abs().clamp(min=1e-3)
+    e = torch.exp(-a)
+    mean = 0.5 * h * (1 - e) / ((1 + e) * a)
+    var = 0.5 * h * (1 - e * e - 2 * a * e) / ((1 + e) ** 2 * a**3)
+    return mean, var
+
+
+def test_cfg3_saddle_and_gamma_full_size_moments(pg, torch):
+    """BASELINE configs[2] at full size through size-independent properties: the saddle sweep (1e8 elements,
+    h ~ U[10, 100], z ~ U[-50, 50]) and the gamma sweep (1e7, h ~ U[0.1, 1]): per element standardised
+    residuals (x - E) / sd have mean 0 and mean square 1 within 4 SE.  Saddle: exact PG moments on h >= 15,
+    where the saddle-point approximation's intrinsic bias is below detection (8-DEFECTS e); gamma: the moments
+    of the 200-term truncated sum (8-DEFECTS f)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(515)
+    n = 100_000_000
+    h = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 90 + 10
+    z = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 100 - 50
+    x = pg.random_polyagamma(h, z, method="saddle", random_state=(616, 0), disable_checks=True)
+    assert bool(torch.isfinite(x).all())
+    mean, var = _pg_moments_t(torch, h, z)
+    cnt, zm, zv = _standardised(x, mean, var, h >= 15)
+    assert cnt > 9e7 and abs(zm) < 4 and abs(zv) < 4, (cnt, zm, zv)
+    del x, mean, var, h, z
+    torch.cuda.empty_cache()
+    n = 10_000_000
+    h = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 0.9 + 0.1
+    z = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 100 - 50
+    x = pg.random_polyagamma(h, z, method="gamma", random_state=(616, 1), disable_checks=True)
+    k = torch.arange(200, device="cuda", dtype=torch.float64)[None, :]
+    s1 = torch.empty(n, device="cuda", dtype=torch.float64)
+    s2 = torch.empty(n, device="cuda", dtype=torch.float64)
+    for lo in range(0, n, 1_000_000):
+        d = np.pi**2 * (k + 0.5) ** 2 + (z[lo:lo + 1_000_000, None] ** 2) / 4
+        s1[lo:lo + 1_000_000] = (1 / d).sum(1)
+        s2[lo:lo + 1_000_000] = (1 / d**2).sum(1)
+    cnt, zm, zv = _standardised(x, 0.5 * h * s1, 0.25 * h * s2)
+    assert abs(zm) < 4 and abs(zv) < 4, (zm, zv)
+
+
+def test_cfg4_full_size_per_bucket_moments(pg, torch):
+    """BASELINE configs[3] (hybrid, h ~ U[0.1, 200], z ~ U[-50, 50]) at 1e8 elements: standardised residuals per
+    method bucket of src/pgm_random.c:105-121 -- normal approximation (moments exact by construction), saddle on
+    h >= 15, alternate on 1 <= h <= 4 (h < 1 inherits the reference's bias, 8-DEFECTS b) -- within 4 SE."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(717)
+    n = 100_000_000
+    h = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 199.9 + 0.1
+    z = torch.rand(n, device="cuda", dtype=torch.float64, generator=g) * 100 - 50
+    x = pg.random_polyagamma(h, z, random_state=(818, 0), disable_checks=True)
+    assert bool(torch.isfinite(x).all())
+    mean, var = _pg_moments_t(torch, h, z)
+    normal = h > 50
+    saddle = ~normal & ((h >= 8) | ((h > 4) & (z <= 4)))
+    alt = ~normal & ~saddle & (h >= 1)
+    for name, mask, least in (("normal", normal, 7e7), ("saddle", saddle & (h >= 15), 1.5e7), ("alternate", alt, 2e6)):
+        cnt, zm, zv = _standardised(x, mean, var, mask)
+        assert cnt > least and abs(zm) < 4 and abs(zv) < 4, (name, cnt, zm, zv)

@@ -70,3 +70,25 @@ def test_even_in_z(oracle):
     x = np.linspace(0.05, 4, 50)
     for name in NAMES:
         assert np.array_equal(oracle.density(name, x, 2.5, 3.0), oracle.density(name, x, 2.5, -3.0))
+
+
+def test_stable_density_restatement_against_300_digit_series():
+    """oracle/stable_density.py (the contour-integration pdf / cdf the CUDA kernels offer as which = 4..7, SURVEY
+    8f-3) against tests/golden/stable_density_golden.npz: the reference's alternating series in 300-digit
+    arithmetic (tests/golden/make_stable_golden.py), on h in {8 .. 200}, z in {0 .. 20}, x = mean + k sd."""
+    import os
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(os.path.dirname(here), "oracle"))
+    import stable_density as S
+
+    g = np.load(os.path.join(here, "golden", "stable_density_golden.npz"))
+    assert g["x"].size >= 100 and set(np.unique(g["h"])) >= {8.0, 40.0, 200.0}
+    worst = 0.0
+    for x, h, z, pdf, cdf, sf in zip(g["x"], g["h"], g["z"], g["pdf"], g["cdf"], g["sf"]):
+        p, c, s = S.pdf_cdf(x, h, z)
+        for got, want in ((p, pdf), (c, cdf), (s, sf)):
+            if want > 1e-290:
+                worst = max(worst, abs(got - want) / want)
+    assert worst < 2e-12, worst
