@@ -61,6 +61,19 @@ make_fill_args(uint64_t seed, uint64_t offset, double* d_out, uint64_t first_ind
     return a;
 }
 
+// product of the extents; false for a negative extent or a product beyond 2^62
+bool
+element_count(int ndim, const int64_t* shape, uint64_t& n)
+{
+    n = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (shape[d] < 0) return false;
+        if (shape[d] != 0 && n > (uint64_t(1) << 62) / (uint64_t)shape[d]) return false;
+        n *= (uint64_t)shape[d];
+    }
+    return true;
+}
+
 // Drop size-1 dimensions and merge neighbours that are contiguous for every operand, so the
 // per-element index decomposition in the kernels is as short as possible.
 // Returns the collapsed ndim; strides arrays are rewritten in place.
@@ -207,11 +220,9 @@ pgm_cuda_random_polyagamma_fill2_strided(uint64_t seed, uint64_t offset, const d
                                          void* stream)
 {
     if (ndim < 0 || ndim > PGM_CUDA_MAX_NDIM) return PGM_CUDA_EINVAL;
+    if (ndim > 0 && (shape == nullptr || h_strides == nullptr || z_strides == nullptr)) return PGM_CUDA_EINVAL;
     uint64_t n = 1;
-    for (int d = 0; d < ndim; ++d) {
-        if (shape[d] < 0) return PGM_CUDA_EINVAL;
-        n *= (uint64_t)shape[d];
-    }
+    if (!element_count(ndim, shape, n)) return PGM_CUDA_EINVAL;
     if (n == 0) return 0;
     if (d_out == nullptr || d_h == nullptr || d_z == nullptr) return PGM_CUDA_EINVAL;
     FillArgs a = make_fill_args(seed, offset, d_out, first_index);
@@ -309,11 +320,10 @@ pgm_cuda_polyagamma_density_strided(int which, const double* d_x, const double* 
                                     const int64_t* z_strides, double* d_out, void* stream)
 {
     if (ndim < 0 || ndim > PGM_CUDA_MAX_NDIM || which < 0 || which > 7) return PGM_CUDA_EINVAL;
+    if (ndim > 0 && (shape == nullptr || x_strides == nullptr || h_strides == nullptr || z_strides == nullptr))
+        return PGM_CUDA_EINVAL;
     uint64_t n = 1;
-    for (int d = 0; d < ndim; ++d) {
-        if (shape[d] < 0) return PGM_CUDA_EINVAL;
-        n *= (uint64_t)shape[d];
-    }
+    if (!element_count(ndim, shape, n)) return PGM_CUDA_EINVAL;
     if (n == 0) return 0;
     if (d_x == nullptr || d_h == nullptr || d_z == nullptr || d_out == nullptr) return PGM_CUDA_EINVAL;
     DensityArgs a;

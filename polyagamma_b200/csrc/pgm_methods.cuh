@@ -241,15 +241,24 @@ struct Alternate {
         double w_last, lg_last;  // record of the remainder piece
     };
 
-    // get_truncation_point (src/pgm_alternate.c:38-70) as a true linear interpolation
+    // get_truncation_point (src/pgm_alternate.c:38-70) as a true linear interpolation.
+    // PGM_TRUNC_SCALE (build-time, default 1) rescales the table: 0.5 gives the acceptance-optimal points (the
+    // reference's generator, scripts/generate_alternate_truncation_pts.py:53-83, doubles the argmin).  The A/B
+    // is in profiles/r2_trunc_table_ab.txt (tools/ab_trunc_table.sh): fewer proposals per sample, but slower on
+    // the B200 -- the smaller t moves proposals to the costlier pieces and lengthens the setup's continued
+    // fraction -- so the reference's table stays.
+#ifndef PGM_TRUNC_SCALE
+#define PGM_TRUNC_SCALE 1.0
+#endif
     static __device__ __forceinline__ double trunc_point(double h)
     {
-        if (h <= 1.0) return c_trunc_f[0];
-        if (h >= 4.0) return c_trunc_f[24];
+        constexpr double ks = PGM_TRUNC_SCALE;
+        if (h <= 1.0) return ks * c_trunc_f[0];
+        if (h >= 4.0) return ks * c_trunc_f[24];
         double pos = (h - 1.0) * 8.0;
         int i = (int)pos;
         double frac = pos - i;
-        return c_trunc_f[i] + (c_trunc_f[i + 1] - c_trunc_f[i]) * frac;
+        return ks * (c_trunc_f[i] + (c_trunc_f[i + 1] - c_trunc_f[i]) * frac);
     }
 
     // the expensive half of set_sampling_parameters (src/pgm_alternate.c:139-176): the mixture

@@ -159,3 +159,25 @@ def test_shard_range_partitions():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(10, 2, 2)
+
+
+def test_argument_checks_need_no_gpu():
+    """Bad arguments are rejected before anything touches the device: NULL shape / strides, an element count
+    that overflows, an unknown `which`."""
+    import ctypes
+
+    from polyagamma_b200 import _lib
+
+    L = _lib.lib()
+    i64 = ctypes.c_int64
+    shape = (i64 * 2)(1 << 40, 1 << 40)
+    st = (i64 * 2)(0, 0)
+    one = ctypes.c_void_p(8)  # never dereferenced
+    assert L.pgm_cuda_random_polyagamma_fill2_strided(1, 0, one, one, _lib.HYBRID, 2, None, st, st, one, 0, None) == _lib.EINVAL
+    assert L.pgm_cuda_random_polyagamma_fill2_strided(1, 0, one, one, _lib.HYBRID, 2, shape, None, st, one, 0, None) == _lib.EINVAL
+    assert L.pgm_cuda_random_polyagamma_fill2_strided(1, 0, one, one, _lib.HYBRID, 2, shape, st, st, one, 0, None) == _lib.EINVAL
+    assert L.pgm_cuda_polyagamma_density_strided(0, one, one, one, 2, shape, st, st, st, one, None) == _lib.EINVAL
+    assert L.pgm_cuda_polyagamma_density_strided(0, one, one, one, 1, None, st, st, st, one, None) == _lib.EINVAL
+    assert L.pgm_cuda_polyagamma_density_strided(8, one, one, one, 0, shape, st, st, st, one, None) == _lib.EINVAL
+    neg = (i64 * 1)(-3)
+    assert L.pgm_cuda_random_polyagamma_fill2_strided(1, 0, one, one, _lib.HYBRID, 1, neg, st, st, one, 0, None) == _lib.EINVAL
