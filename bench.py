@@ -465,7 +465,7 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
     fp64_nominal = 148 * 64 * 2 * sm_max_mhz * 1e6 / 1e12  # 148 SMs x 64 DFMA/clk x 2 flops
-    fp64_peak = max(fp64_peak_measured, 0.0) or fp64_nominal
+    fp64_peak = max(fp64_peak_measured, fp64_nominal)  # the larger of the two: never flatter the fraction
     costs = kernel_costs(args.config)
     active = {k: v for k, v in kernels.items() if v[1] and v[0] > 0}
     total_kernel_ms = sum(v[0] for v in active.values())
@@ -499,8 +499,8 @@ def main():
             "fp64": fp64, "hbm": hbm,
             "fp64_peak": {"measured_tflops": fp64_peak_measured, "nominal_tflops": fp64_nominal,
                           "note": "measured: 16-chain DFMA microbenchmark in this process (builder-measured: "
-                                  "MEASURED_PEAKS.json has no FP64 entry); nominal: 148 SMs x 64 DFMA/clk x 2 x max SM clock; "
-                                  "fractions use the measured one"},
+                                  "MEASURED_PEAKS.json has no FP64 entry); nominal: 148 SMs x 64 DFMA/clk x 2 x max SM clock "
+                                  "(tools/dmma_peak.cu reaches 37.0 with DMMA); fractions use the LARGER of the two"},
             "timing": "per-kernel times: the same K steps run once more with CUDA events around every launch and "
                       "the kernels serialised (PGM_CUDA_NO_OVERLAP=1), outside the headline timed region",
             "kernel_ms_per_step": {k: v[0] / args.steps for k, v in active.items()},
