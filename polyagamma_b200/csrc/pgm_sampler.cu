@@ -358,10 +358,10 @@ struct __align__(16) TileSmem {
     uint32_t c_idx[kCarryCap];  //   element index inside the pass,
     uint32_t c_pos[kCarryCap];  //   Philox word position
     uint16_t list[kTile];       // local indices, grouped by bucket
-    uint32_t cnt[kNumBuckets];    // elements of each bucket in this tile
+    uint32_t cnt2[2][kNumBuckets];   // elements of each bucket in this tile   (two sets: a tile uses the set of its
+    uint32_t next2[2][kNumBuckets];  // in-tile buckets: work counter            parity and clears the other one)
     uint32_t off[kNumBuckets];    // start of each bucket's group in list
     uint32_t gbase[kNumBuckets];  // list buckets: start of this tile's range in the global list
-    uint32_t next[kNumBuckets];   // in-tile buckets: work counter
     uint32_t c_tail;              // ring: records pushed so far (monotonic; slot = count mod kCarryCap)
 };
 
@@ -464,6 +464,41 @@ saddle_round(const FillArgs& a, bool compat, uint32_t tile0, uint32_t tile_n, Ti
     return rejected;
 }
 
+// The operands of one full tile of contiguous, 16-byte aligned arrays (or scalars): thread t takes the pairs
+// j * T + t, j = 0..3, with 16-byte loads.
+static __device__ __forceinline__ void
+load_tile_operands(const FillArgs& a, uint64_t g0, uint32_t tid, double (&hv)[8], double (&zv)[8])
+{
+    if (a.h != nullptr && a.h_stride != 0) {
+        const double2* p = reinterpret_cast<const double2*>(a.h + g0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2 v = __ldg(p + j * kTileThreads + tid);
+            hv[2 * j] = v.x;
+            hv[2 * j + 1] = v.y;
+        }
+    }
+    else {  // one value for the whole call: a host scalar, or a one-element device operand
+        const double v = a.h ? __ldg(a.h) : a.h_scalar;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) hv[k] = v;
+    }
+    if (a.z != nullptr && a.z_stride != 0) {
+        const double2* p = reinterpret_cast<const double2*>(a.z + g0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double2 v = __ldg(p + j * kTileThreads + tid);
+            zv[2 * j] = v.x;
+            zv[2 * j + 1] = v.y;
+        }
+    }
+    else {
+        const double v = a.z ? __ldg(a.z) : a.z_scalar;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) zv[k] = v;
+    }
+}
+
 // `method` is the requested sampler (kHybrid: src/pgm_random.c:105-121 decides per element).
 // VEC: h and z are contiguous, 16-byte aligned arrays (or scalars) and every tile of the launch is full.
 // The launch covers tiles tile_first .. tile_first + tile_count - 1 of the pass.
@@ -479,51 +514,30 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
     const bool compat = a.compat != 0;
     uint32_t c_head = 0, c_tail = 0;  // ring: records consumed / pushed so far (block-uniform; slot = count mod capacity)
     if (tid == 0) S.c_tail = 0;       // (the shared copy hands out the slots of a round's pushes)
+    if (tid < 2 * kNumBuckets) {
+        (&S.cnt2[0][0])[tid] = 0;
+        (&S.next2[0][0])[tid] = 0;
+    }
+    __syncthreads();
 
-    for (uint32_t tile = blockIdx.x; tile < tile_count; tile += gridDim.x) {
+    // Barriers of a tile: B1 after the classification, B3 after the local lists, one per saddle round, BA after
+    // the in-tile sampling, BE after the tile's stores.  The operands of the block's NEXT tile are prefetched into
+    // L2 while this one is sampled (holding them in registers across the loop makes ptxas spill them at once);
+    // the reservation in the global lists is made by the first warp at the start of the normal-approximation
+    // phase, where the other warps do not wait for it.
+    uint32_t parity = 0;
+    for (uint32_t tile = blockIdx.x; tile < tile_count; tile += gridDim.x, parity ^= 1u) {
         const uint32_t tile0 = (tile_first + tile) * kTile;  // first element of the tile inside the pass
         const uint32_t tn = VEC ? (uint32_t)kTile : min((uint32_t)kTile, n - tile0);
         const uint64_t g0 = a.base + tile0;
-        if (tid < kNumBuckets) {
-            S.cnt[tid] = 0;
-            S.next[tid] = 0;
-        }
-        __syncthreads();
+        uint32_t* const cnt = S.cnt2[parity];
+        uint32_t* const next = S.next2[parity];
 
         // ---- 1. load + classify.  Thread t owns local elements j * 2T + 2 t + {0, 1}, j = 0..3 ----
         uint32_t where[kTileItems / 2] = {0, 0, 0, 0};  // per owned element: bucket (4 bits) | position in its group (12 bits)
         {
             double hv[kTileItems], zv[kTileItems];
-            if (VEC) {
-                if (a.h != nullptr && a.h_stride != 0) {
-                    const double2* p = reinterpret_cast<const double2*>(a.h + g0);
-#pragma unroll
-                    for (int j = 0; j < kTileItems / 2; ++j) {
-                        const double2 v = __ldg(p + j * kTileThreads + tid);
-                        hv[2 * j] = v.x;
-                        hv[2 * j + 1] = v.y;
-                    }
-                }
-                else {  // one value for the whole call: a host scalar, or a one-element device operand
-                    const double v = a.h ? __ldg(a.h) : a.h_scalar;
-#pragma unroll
-                    for (int k = 0; k < kTileItems; ++k) hv[k] = v;
-                }
-                if (a.z != nullptr && a.z_stride != 0) {
-                    const double2* p = reinterpret_cast<const double2*>(a.z + g0);
-#pragma unroll
-                    for (int j = 0; j < kTileItems / 2; ++j) {
-                        const double2 v = __ldg(p + j * kTileThreads + tid);
-                        zv[2 * j] = v.x;
-                        zv[2 * j + 1] = v.y;
-                    }
-                }
-                else {
-                    const double v = a.z ? __ldg(a.z) : a.z_scalar;
-#pragma unroll
-                    for (int k = 0; k < kTileItems; ++k) zv[k] = v;
-                }
-            }
+            if (VEC) load_tile_operands(a, g0, tid, hv, zv);
             else {
                 // partial tile, or strided / broadcast / unaligned operands: staged through shared memory (one
                 // copy of the general index arithmetic)
@@ -561,7 +575,7 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
                 const uint32_t same = __match_any_sync(0xffffffffu, b);
                 const int leader = __ffs(same) - 1;
                 uint32_t r = 0;
-                if (valid && (int)lane == leader) r = atomicAdd(&S.cnt[b], (uint32_t)__popc(same));
+                if (valid && (int)lane == leader) r = atomicAdd(&cnt[b], (uint32_t)__popc(same));
                 r = __shfl_sync(0xffffffffu, r, leader) + __popc(same & lt);
                 where[k >> 1] |= (b | (r << 4)) << (16 * (k & 1));
             }
@@ -573,17 +587,27 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
         }
         __syncthreads();
 
-        // ---- 2. group offsets; reserve the tile's range in each global list; write the local lists ----
-        if (tid < kNumBuckets) {
+        // ---- 2. group offsets (every warp works them out for itself: identical values, no barrier); clear the
+        // other set of counters for the next tile; write the local lists ----
+        if (lane < kNumBuckets) {
             uint32_t off = 0;
-            for (uint32_t q = 0; q < tid; ++q) off += S.cnt[q];
-            S.off[tid] = off;
-            const uint32_t c = S.cnt[tid];
-            uint32_t base = 0;
-            if (c != 0 && list_slot((int)tid) >= 0) base = atomicAdd(&ctl[kCtlCount + tid], c);
-            S.gbase[tid] = base;
+            for (uint32_t q = 0; q < lane; ++q) off += cnt[q];
+            S.off[lane] = off;
+            if (tid < kNumBuckets) {
+                S.cnt2[parity ^ 1u][tid] = 0;
+                S.next2[parity ^ 1u][tid] = 0;
+            }
         }
-        __syncthreads();
+        __syncwarp();
+        if (VEC && tile + gridDim.x < tile_count) {
+            // one 128-byte line of the next tile per thread: the first half of the block takes h, the second z
+            const double* src = tid < kTileThreads / 2 ? a.h : a.z;
+            const bool arr = tid < kTileThreads / 2 ? a.h_stride != 0 : a.z_stride != 0;
+            if (src != nullptr && arr) {
+                const double* q = src + g0 + (uint64_t)gridDim.x * kTile + 16u * (tid & (kTileThreads / 2 - 1));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+            }
+        }
 #pragma unroll
         for (int k = 0; k < kTileItems; ++k) {
             const uint32_t e = (k >> 1) * (2 * kTileThreads) + 2 * tid + (k & 1);
@@ -591,25 +615,7 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
             const uint32_t q = w & 15u;
             if (q != kBucketNone) S.list[S.off[q] + (w >> 4)] = (uint16_t)e;
         }
-        __syncthreads();
-
-        // ---- divergent buckets: append (index, h, z) to the global lists ----
-#pragma unroll 1
-        for (int q = 0; q < kNumBuckets; ++q) {
-            const int slot = list_slot(q);
-            if (slot < 0) continue;
-            const uint32_t c = S.cnt[q];
-            if (c == 0) continue;  // block-uniform
-            const uint32_t off = S.off[q];
-            const size_t dst = (size_t)slot * el.stride + S.gbase[q];
-            for (uint32_t i = tid; i < c; i += kTileThreads) {
-                const uint32_t e = S.list[off + i];
-                el.idx[dst + i] = tile0 + e;
-                el.h[dst + i] = S.hout[e];
-                el.z[dst + i] = S.z[e];
-                S.hout[e] = NAN;  // pending: written by the bucket's own kernel
-            }
-        }
+        __syncthreads();  // B3
 
         // ---- 3. in-tile buckets ----
         const uint64_t index0 = a.first_index + g0;
@@ -617,7 +623,7 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
             // saddle queue: full rounds while there is a block-load of work, the rest is carried.  c_tail (how
             // many records were ever pushed) is tracked in a register as well: a round's barrier counts its
             // rejections, so the block agrees on the queue length without reading the shared counter.
-            const uint32_t m = S.cnt[kBSaddleLeft];
+            const uint32_t m = cnt[kBSaddleLeft];
             const uint16_t* ls = S.list + S.off[kBSaddleLeft];
             uint32_t l_head = 0;
             for (;;) {
@@ -642,14 +648,22 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
             c_tail += left;
             if (tid == 0) S.c_tail = c_tail;  // (the next push is at least two barriers away)
         }
+        if (tid < kNumBuckets) {
+            // reserve the tile's range in each global list: the first warp waits for the answer while the others
+            // are already taking normal-approximation work
+            const uint32_t c = cnt[tid];
+            uint32_t reserved = 0;
+            if (c != 0 && list_slot((int)tid) >= 0) reserved = atomicAdd(&ctl[kCtlCount + tid], c);
+            S.gbase[tid] = reserved;
+        }
         {
             // normal approximation: work queue of batches of 64 elements
-            const uint32_t cn = S.cnt[kBNormal];
+            const uint32_t cn = cnt[kBNormal];
             const uint16_t* ln = S.list + S.off[kBNormal];
             const uint32_t nitems = (cn + 63u) >> 6;
             for (;;) {
                 uint32_t it = 0;
-                if (lane == 0) it = atomicAdd(&S.next[kBNormal], 1u);
+                if (lane == 0) it = atomicAdd(&next[kBNormal], 1u);
                 it = __shfl_sync(0xffffffffu, it, 0);
                 if (it >= nitems) break;
                 const uint32_t i = (it << 6) + lane;
@@ -663,8 +677,27 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
                 }
             }
         }
-        __syncthreads();
-        // ---- 4. the tile's outputs ----
+        __syncthreads();  // BA
+
+        // ---- 4. divergent buckets: append (index, h, z) to the global lists (their positions in the tile's
+        // output are written by the bucket's own kernel, which runs after this one) ----
+#pragma unroll 1
+        for (int q = 0; q < kNumBuckets; ++q) {
+            const int slot = list_slot(q);
+            if (slot < 0) continue;
+            const uint32_t c = cnt[q];
+            if (c == 0) continue;  // block-uniform
+            const uint32_t off = S.off[q];
+            const size_t dst = (size_t)slot * el.stride + S.gbase[q];
+#pragma unroll 1
+            for (uint32_t i = tid; i < c; i += kTileThreads) {
+                const uint32_t e = S.list[off + i];
+                el.idx[dst + i] = tile0 + e;
+                el.h[dst + i] = S.hout[e];
+                el.z[dst + i] = S.z[e];
+            }
+        }
+        // ---- 5. the tile's outputs ----
         double* out = a.out + g0;
         if (tn == (uint32_t)kTile && ((uintptr_t)out & 15) == 0) {
 #pragma unroll
@@ -676,8 +709,9 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
         else {
             for (uint32_t e = tid; e < tn; e += kTileThreads) out[e] = S.hout[e];
         }
-        // (the next tile's first barrier orders these stores before the block's later stores to carried
-        // elements' positions, and before the tile's shared memory is overwritten)
+        // BE: the appends have read the tile before the next one overwrites it (and these stores are ordered
+        // before the block's later stores to carried elements' positions)
+        __syncthreads();
     }
     // the block's last carried elements: partial rounds until the ring is empty
     __syncthreads();
