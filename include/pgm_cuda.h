@@ -171,7 +171,8 @@ uint64_t pgm_cuda_launch_count(void);
 /* Per-kernel device time, for roofline accounting.  Between _begin and _end every kernel this
  * library launches is bracketed by CUDA events on its own stream; _end synchronises those
  * events and returns, per kernel kind, the summed milliseconds and the launch count.
- * Kinds: 0 unused (round 1: the bucketing kernel), 1 the one-launch kernel of small fills, 2 the tile
+ * Kinds: 0 the drain kernel (every divergent bucket of a mid-size fill in one launch), 1 the one-launch
+ * kernel of small fills, 2 the tile
  * kernel (classification, the in-tile normal / left-saddle / devroye draws, list compaction);
  * sampling kernels over a list or an identity range: 3 devroye (both proposal variants), 4 alternate,
  * 5 saddle (both envelope pieces), 6 saddle-left (left piece only), 7 unused, 8 alternate-left (left

@@ -143,7 +143,7 @@ def launch_count() -> int:
 
 
 _METHOD_KERNELS = ("devroye", "alternate", "saddle", "saddle_left", "saddle_far", "alternate_left", "saddle_mid")
-KERNEL_KINDS = (("classify", "small", "tile") + _METHOD_KERNELS + ("normal", "gamma", "density") +
+KERNEL_KINDS = (("drain", "small", "tile") + _METHOD_KERNELS + ("normal", "gamma", "density") +
                 tuple("setup_" + k for k in _METHOD_KERNELS) + ("gibbs_xbeta", "gibbs_gram"))
 
 

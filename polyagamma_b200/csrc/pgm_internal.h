@@ -63,7 +63,7 @@ int launch_test_math(int which, const double* d_in, size_t n, double* d_out, cud
 
 // kernel kinds reported by pgm_cuda_profile_end
 enum : int {
-    kKindClassify = 0,  // (round 1: the one-pass bucketing kernel; unused)
+    kKindDrain = 0,     // every divergent bucket of a mid-size fill in one launch
     kKindSmall = 1,     // the one-launch kernel for small fills
     kKindTile = 2,      // tile kernel: classify + in-tile normal / far saddle / devroye + list compaction
     // sampling kernels: + 0 devroye, 1 alternate, 2 saddle, 3 saddle-left, 4 saddle-far, 5 alternate-left,

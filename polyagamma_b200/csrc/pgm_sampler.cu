@@ -941,6 +941,58 @@ small_kernel(FillArgs a, uint32_t n, int method)
     a.out[g] = v;
 }
 
+// ---------------------------------------------------------------------------------------
+// drain kernel: every divergent bucket of a pass in ONE launch -- the path for fills between the one-launch
+// kernel and a few 10^5 elements, where seven bucket launches on three streams and their event joins cost more
+// than the sampling itself.  The lists of the pass form one index space (list after list); a thread takes the
+// entries t, t + threads, ... and runs each to completion with the bucket's make_record / load / step code: the
+// draws are the pipeline's, bit for bit.  Good while the lists are short (a hybrid fill with mixed shapes: 4 %
+// of the elements); with long lists the lanes of a warp wait for the slowest element and the pipeline's
+// refilling kernels win, so the path stops at 2^18 elements (tools/perf_mid.py, profiles/r2_perf_mid.txt; the
+// same five lists through the persistent-lane loop inside one kernel were measured too, and lose to both).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+drain_kernel(FillArgs a, ElemLists el, const uint32_t* __restrict__ ctl)
+{
+    const bool compat = a.compat != 0;
+    const uint32_t k0 = a.key.k0, k1 = a.key.k1;
+    // end of each list slot's range in the common index space
+    uint32_t end[kNumListSlots];
+    const int bucket_of_slot[kNumListSlots] = {kBAlternate, kBSaddleFull, kBAlternateLeft, kBDevroye, kBDevroyeMSH};
+    uint32_t total = 0;
+#pragma unroll
+    for (int sl = 0; sl < kNumListSlots; ++sl) {
+        total += ctl[kCtlCount + bucket_of_slot[sl]];
+        end[sl] = total;
+    }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < total; p += stride) {
+        int sl = 0;
+        uint32_t first = 0;
+#pragma unroll
+        for (int j = 0; j + 1 < kNumListSlots; ++j) {
+            if (p >= end[j]) {
+                sl = j + 1;
+                first = end[j];
+            }
+        }
+        const size_t o = (size_t)sl * el.stride + (p - first);
+        const uint32_t idx = el.idx[o];
+        const double h = el.h[o], z = el.z[o];
+        const uint64_t index = a.first_index + a.base + idx;
+        double v;
+        switch (sl) {  // (list_slot())
+            case 0: v = run_one<Alternate>(k0, k1, index, h, z, compat); break;
+            case 1: v = run_one<SaddleFull>(k0, k1, index, h, z, compat); break;
+            case 2: v = run_one<AlternateLeft>(k0, k1, index, h, z, compat); break;
+            case 3: v = run_one<DevroyeT<kDevroyePair>>(k0, k1, index, h, z, compat); break;
+            default: v = run_one<DevroyeT<kDevroyeMSH>>(k0, k1, index, h, z, compat); break;
+        }
+        a.out[a.base + idx] = v;
+    }
+}
+static_assert(kNumListSlots == 5, "drain_kernel's switch follows list_slot()");
+
 // fills the saddle tables (one thread per entry): the starting points of the FULL setup's right solve, and
 // the Hermite pieces of Gr and Hr (pgm_methods.cuh)
 __global__ void
@@ -1203,6 +1255,20 @@ multi_min()
     return 1ull << env_int("PGM_CUDA_MULTI_MIN_LOG2", 0, 40, 16);
 }
 
+// Largest fill that takes the two-launch path (tile kernel + drain kernel).  PGM_CUDA_MID_MAX overrides it
+// (0 disables the path); tools/perf_mid.py has the measurements behind the default.
+constexpr uint64_t kMidMaxDefault = 1ull << 18;
+static uint64_t
+mid_max()
+{
+    const char* e = getenv("PGM_CUDA_MID_MAX");
+    if (e == nullptr || *e == '\0') return kMidMaxDefault;
+    char* end = nullptr;
+    unsigned long long v = strtoull(e, &end, 10);
+    if (end == e) return kMidMaxDefault;
+    return v > (1ull << 25) ? (1ull << 25) : (uint64_t)v;
+}
+
 // fill2 over arrays, n <= 2^31: passes of tile_kernel (caller's stream) + the divergent buckets' kernels (helper
 // streams).  There are two sets of element lists: pass k appends to set k & 1 while the bucket kernels of pass
 // k - 1 drain the other set beside it; the record regions (one per bucket) are shared by the sets, so a
@@ -1235,6 +1301,10 @@ fill_arrays(const DeviceInfo& d, FillArgs a, uint64_t n, int m, cudaStream_t s)
     int lg = first_chunk_log2(n);
     const bool no_overlap = getenv("PGM_CUDA_NO_OVERLAP") != nullptr;
     const bool any_buckets = true;
+    // one pass, and small enough that launches and joins outweigh the divergence of a run-to-completion kernel:
+    // tile kernel + drain kernel on the caller's stream, no records, no helper streams
+    const bool mid_ok = !no_overlap && n <= mid_max();
+    bool mid = false;
     uint64_t chunk = 0;
     uint32_t cap = 0;
     size_t list_bytes = 0, rec_bytes = 0;
@@ -1244,11 +1314,12 @@ fill_arrays(const DeviceInfo& d, FillArgs a, uint64_t n, int m, cudaStream_t s)
     char* ws = nullptr;
     for (;;) {
         chunk = 1ull << lg;
+        mid = mid_ok && n <= chunk;
         const uint64_t cmax = n < chunk ? n : chunk;
         nsets = (n > chunk && !no_overlap && any_buckets) ? 2 : 1;
         cap = (uint32_t)((cmax + 63) & ~uint64_t(63));
         list_bytes = any_buckets ? align256((size_t)cap * kNumListSlots * (sizeof(uint32_t) + 2 * sizeof(double))) : 0;
-        rec_bytes = any_buckets ? align256((size_t)cap * kRecFields * sizeof(double)) : 0;
+        rec_bytes = (any_buckets && !mid) ? align256((size_t)cap * kRecFields * sizeof(double)) : 0;
         err = (cudaError_t)scratch_alloc((void**)&ws, nsets * (ctl_bytes + list_bytes) + rec_bytes, s);
         if (err == cudaSuccess) break;
         (void)cudaGetLastError();  // clear the sticky-free allocation error and retry smaller
@@ -1315,6 +1386,18 @@ fill_arrays(const DeviceInfo& d, FillArgs a, uint64_t n, int m, cudaStream_t s)
     };
 
     const uint64_t npass = (n + chunk - 1) / chunk;
+    if (mid) {
+        tile_pass(a, (uint32_t)n, set[0], s);
+        {
+            ScopedKernelTimer timer(kKindDrain, s);
+            const uint64_t want = (n + 255) / 256, most = (uint64_t)d.sms * 8;
+            drain_kernel<<<(unsigned)(want < most ? want : most), 256, 0, s>>>(a, set[0].el, set[0].ctl);
+            count_launch(1);
+            evlog("drain_kernel", 0, s);
+        }
+        cudaFreeAsync(ws, s);
+        return (int)cudaGetLastError();
+    }
     const bool multi = !no_overlap && any_buckets && (nsets == 2 || n >= multi_min());
     if (!multi) {
         for (uint64_t k = 0; k < npass; ++k) {

@@ -72,18 +72,20 @@ def _stream():
 
 
 @pytest.mark.parametrize("n", SIZES)
-@pytest.mark.parametrize("small_max", [None, "0"])
+@pytest.mark.parametrize("small_max", [None, "0", "mid"])
 @pytest.mark.parametrize("shift", [0, 1])
 def test_fill2_stays_inside_its_output(n, small_max, shift, monkeypatch):
-    """hybrid fill2 through the one-launch kernel (default, n <= 2^16) and the bucketed pipeline
-    (PGM_CUDA_SMALL_MAX=0, 2^13-element passes so that several passes and a ragged last one run), on
-    16-byte aligned operands (vector loads in the classify pass) and on 8-byte aligned ones."""
+    """hybrid fill2 through the one-launch kernel (default, n <= 2^17), the bucketed pipeline
+    (PGM_CUDA_SMALL_MAX=0, 2^13-element passes so that several passes and a ragged last one run) and the
+    two-launch path of mid-size fills ("mid": tile kernel + drain kernel), on 16-byte aligned operands (vector
+    loads in the classify pass) and on 8-byte aligned ones."""
     torch = _torch()
     from polyagamma_b200 import _lib
 
     if small_max is not None:
-        monkeypatch.setenv("PGM_CUDA_SMALL_MAX", small_max)
-        monkeypatch.setenv("PGM_CUDA_CHUNK_LOG2", "13")
+        monkeypatch.setenv("PGM_CUDA_SMALL_MAX", "0")
+        if small_max == "0":
+            monkeypatch.setenv("PGM_CUDA_CHUNK_LOG2", "13")
     L = _lib.lib()
     h, z = _inputs(n, n, shift)
     buf, out = _banded(n, shift=shift)

@@ -383,8 +383,9 @@ def test_c_abi_direct_call(torch, oracle):
 @pytest.mark.parametrize("method", [None, "devroye", "alternate", "saddle"])
 @pytest.mark.parametrize("compat", [False, True])
 def test_small_fill_path_equals_pipeline(pg, torch, monkeypatch, method, compat):
-    """Fills of up to 2^16 elements take ONE launch (a thread per element through the same per-bucket
-    code); the result must be bit-identical to the bucketed pipeline's, arrays and scalars."""
+    """Fills of up to 2^17 elements take ONE launch (a thread per element through the same per-bucket
+    code), fills of up to 2^20 two (tile kernel + drain kernel); both results must be bit-identical to the
+    bucketed pipeline's, arrays and scalars."""
     rng = np.random.default_rng(17)
     n = 60_001
     if method == "devroye":
@@ -401,13 +402,19 @@ def test_small_fill_path_equals_pipeline(pg, torch, monkeypatch, method, compat)
     h[:4] = [np.nan, -2.0, np.inf, 0.0]
     kw = dict(method=method, random_state=(99, 7), disable_checks=True, ref_compat=compat)
     monkeypatch.setenv("PGM_CUDA_SMALL_MAX", "0")
+    monkeypatch.setenv("PGM_CUDA_MID_MAX", "0")
     want = pg.random_polyagamma(h, z, **kw)
     want_s = pg.random_polyagamma(2.5 if method != "devroye" else 3.0, 1.25, size=20_000, **kw)
+    monkeypatch.delenv("PGM_CUDA_MID_MAX")
+    mid = pg.random_polyagamma(h, z, **kw)
+    mid_s = pg.random_polyagamma(2.5 if method != "devroye" else 3.0, 1.25, size=20_000, **kw)
     monkeypatch.delenv("PGM_CUDA_SMALL_MAX")
     got = pg.random_polyagamma(h, z, **kw)
     got_s = pg.random_polyagamma(2.5 if method != "devroye" else 3.0, 1.25, size=20_000, **kw)
     assert np.array_equal(got, want, equal_nan=True)
     assert np.array_equal(got_s, want_s)
+    assert np.array_equal(mid, want, equal_nan=True)
+    assert np.array_equal(mid_s, want_s)
 
 
 def test_saddle_table(torch):
