@@ -147,6 +147,13 @@ int pgm_cuda_polyagamma_density_strided(int which, const double* d_x, const doub
 int pgm_cuda_polyagamma_density_host(int which, const double* x, int x_stride, const double* h, int h_stride,
                                      const double* z, int z_stride, size_t n, double* out, int device);
 
+/* A device result on its way to PAGEABLE host memory -- what the reference's front-end returns is a freshly
+ * allocated numpy array (polyagamma/_polyagamma.pyx:452-472).  d_src[0..n) -> dst[0..n): chunks go through
+ * pinned bounce buffers on the device's ring of streams and are moved into `dst` by several host threads (the
+ * first touch of a new array is page-fault bound: one thread manages ~2 GB/s).  Waits for the work queued on
+ * `stream` before it reads d_src; returns when dst is complete. */
+int pgm_cuda_download(double* dst, const double* d_src, size_t n, void* stream);
+
 /* ---- next row of the path: the logistic-regression Gibbs omega-step ---------- */
 /* The caller pattern of the batched fill (README.md:146-148; Polson, Scott & Windle 2013):
  *     psi = X beta;   omega_i ~ PG(n_i, psi_i);   G = X^T diag(omega) X

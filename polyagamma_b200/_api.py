@@ -318,7 +318,7 @@ def random_polyagamma(h=1.0, z=0.0, *, size=None, out=None, method=None, disable
                 raise ValueError("negative dimensions are not allowed")
             dev = _device_of(device=device)
             res = _fill_scalar_device(seed, offset, ch, cz, mid, n, dev, fi).reshape(shape)
-            return res if device is not None else res.cpu().numpy()
+            return res if device is not None else _to_numpy(res, dev)
         if has_out:
             if _is_device_array(out):
                 dev = _device_of(out, device=device)
@@ -448,7 +448,7 @@ def _fill_arrays_host(seed, offset, harr, zarr, shape, mid, arr=None, first_inde
         return res
     ht = torch.from_numpy(harr).to(dev)
     zt = torch.from_numpy(zarr).to(dev)
-    return _fill_arrays_device(seed, offset, ht, zt, tuple(shape), mid, dev, first_index=first_index).cpu().numpy()
+    return _to_numpy(_fill_arrays_device(seed, offset, ht, zt, tuple(shape), mid, dev, first_index=first_index), dev)
 
 
 # ------------------------------------------------------------------------------------------
@@ -491,7 +491,21 @@ def _density(kind, x, h, z, return_log, device, stable=False):
         return float(out.item())
     if on_device:
         return out
-    return out.cpu().numpy()
+    return _to_numpy(out, dev)
+
+
+def _to_numpy(t, dev):
+    """A device result as a new numpy array.  Large results go through the library's pinned bounce buffers and
+    several host threads (``pgm_cuda_download``): a plain ``.cpu()`` into fresh pageable memory runs at the
+    page-fault rate of one thread."""
+    if t.numel() < (1 << 18) or not t.is_contiguous():
+        return t.cpu().numpy()
+    res = np.empty(tuple(t.shape), dtype=np.float64)
+    with _torch().cuda.device(dev):
+        rc = _lib.lib().pgm_cuda_download(ctypes.c_void_p(res.ctypes.data), ctypes.c_void_p(t.data_ptr()), t.numel(),
+                                          _stream_ptr(dev))
+    _lib.check(rc, "pgm_cuda_download")
+    return res
 
 
 def polyagamma_pdf(x, h=1.0, z=0.0, return_log=False, *, device=None, stable=False):

@@ -34,6 +34,7 @@ EXPORTS = (
     "pgm_cuda_polyagamma_logcdf",
     "pgm_cuda_polyagamma_density_strided",
     "pgm_cuda_polyagamma_density_host",
+    "pgm_cuda_download",
     "pgm_cuda_logistic_omega_step",
     "pgm_cuda_launch_count",
     "pgm_cuda_profile_begin",
@@ -92,6 +93,8 @@ def lib() -> ctypes.CDLL:
     L.pgm_cuda_polyagamma_density_strided.argtypes = [i, vp, vp, vp, i, p64, p64, p64, p64, vp, vp]
     L.pgm_cuda_polyagamma_density_host.restype = i
     L.pgm_cuda_polyagamma_density_host.argtypes = [i, vp, i, vp, i, vp, i, sz, vp, i]
+    L.pgm_cuda_download.restype = i
+    L.pgm_cuda_download.argtypes = [vp, vp, sz, vp]
     L.pgm_cuda_logistic_omega_step.restype = i
     L.pgm_cuda_logistic_omega_step.argtypes = [u64, u64, vp, sz, i, sz, vp, vp, d, i, vp, vp, vp, u64, vp]
     L.pgm_cuda_launch_count.restype = u64

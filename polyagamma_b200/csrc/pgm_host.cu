@@ -16,6 +16,8 @@
 
 #include <atomic>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "../../include/pgm_cuda.h"
 #include "pgm_internal.h"
@@ -54,6 +56,8 @@ struct Ring {
     cudaStream_t streams[kStreams] = {};
     cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_join[kStreams] = {};
     double* buf[kStreams][kOperands] = {};
+    double* pin[kStreams] = {};  // pinned bounce buffers of pgm_cuda_download (results on their way to pageable memory)
+    size_t pin_cap = 0;
     std::atomic<double> last_ms{0.0};
 };
 Ring g_rings[64];
@@ -68,6 +72,11 @@ ring_free_buffers(Ring& r)
             p = nullptr;
         }
     r.cap = 0;
+    for (auto& p : r.pin) {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+    }
+    r.pin_cap = 0;
 }
 
 void
@@ -186,6 +195,32 @@ queue_fill_chunk(Ring& r, int slot, const HostFill& f, size_t off, size_t cn, ui
     }
     if (int rc = pgm::launch_fill(a, cn, f.method, s)) return rc;
     return (int)cudaMemcpyAsync(f.out + off, r.buf[slot][3], cn * sizeof(double), cudaMemcpyDeviceToHost, s);
+}
+
+// memcpy by several host threads: the destination is usually a freshly allocated array, and its first touch
+// (page faults) is what a single thread cannot do faster than ~2 GB/s
+void
+parallel_memcpy(double* dst, const double* src, size_t n)
+{
+    constexpr size_t kMinPerThread = size_t(1) << 18;  // 2 MiB
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t nt = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1);
+    if (n / kMinPerThread < nt) nt = n / kMinPerThread;
+    if (nt <= 1) {
+        memcpy(dst, src, n * sizeof(double));
+        return;
+    }
+    // split on page boundaries of the destination
+    const size_t per = ((n + nt - 1) / nt + 511) & ~size_t(511);
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nt; ++t) {
+        const size_t lo = t * per;
+        if (lo >= n) break;
+        const size_t cnt = (n - lo) < per ? (n - lo) : per;
+        pool.emplace_back([=] { memcpy(dst + lo, src + lo, cnt * sizeof(double)); });
+    }
+    memcpy(dst, src, (per < n ? per : n) * sizeof(double));
+    for (auto& th : pool) th.join();
 }
 
 // ---- one draw / a handful of points: mapped pinned memory, one launch --------------------------------------
@@ -435,6 +470,63 @@ pgm_cuda_polyagamma_density_host(int which, const double* x, int x_stride, const
         rc = pgm::launch_density(which, a, cn, s);
         if (rc == 0) rc = (int)cudaMemcpyAsync(out + off, r.buf[slot][3], cn * sizeof(double), cudaMemcpyDeviceToHost, s);
     }
+    const int drc = ring_drain(r);
+    if (rc == 0) rc = drc;
+    if (rc != 0) (void)cudaGetLastError();
+    return rc;
+}
+
+int
+pgm_cuda_download(double* dst, const double* d_src, size_t n, void* stream)
+{
+    if (n == 0) return 0;
+    if (dst == nullptr || d_src == nullptr) return PGM_CUDA_EINVAL;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Ring& r = g_rings[dev & 63];
+    std::lock_guard<std::mutex> lock(r.mu);
+    int rc = ring_prepare(r, 0, 0);
+    if (rc != 0) return rc;
+    constexpr size_t kPinChunk = size_t(1) << 22;  // 32 MiB per bounce buffer
+    const size_t chunk = n < kPinChunk ? n : kPinChunk;
+    cudaError_t e = cudaSuccess;
+    if (r.pin_cap < chunk) {
+        for (auto& p : r.pin) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+        }
+        r.pin_cap = 0;
+        for (int i = 0; i < kStreams && e == cudaSuccess; ++i) e = cudaHostAlloc((void**)&r.pin[i], chunk * sizeof(double), cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            for (auto& p : r.pin) {
+                if (p) cudaFreeHost(p);
+                p = nullptr;
+            }
+            (void)cudaGetLastError();
+            return (int)e;
+        }
+        r.pin_cap = chunk;
+    }
+    // the producer's stream has to be done with d_src before the ring's streams read it
+    if ((e = cudaEventRecord(r.ev_join[0], (cudaStream_t)stream)) != cudaSuccess) return (int)e;
+    for (int i = 0; i < kStreams; ++i) cudaStreamWaitEvent(r.streams[i], r.ev_join[0], 0);
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    auto land = [&](size_t c) {  // chunk c has arrived in its bounce buffer: move it to the caller's array
+        const int slot = (int)(c % kStreams);
+        const cudaError_t es = cudaStreamSynchronize(r.streams[slot]);
+        if (es != cudaSuccess) return (int)es;
+        const size_t off = c * chunk, cn = (n - off) < chunk ? (n - off) : chunk;
+        parallel_memcpy(dst + off, r.pin[slot], cn);
+        return 0;
+    };
+    for (size_t c = 0; c < nchunks && rc == 0; ++c) {
+        const int slot = (int)(c % kStreams);
+        if (c >= (size_t)kStreams) rc = land(c - kStreams);
+        if (rc != 0) break;
+        const size_t off = c * chunk, cn = (n - off) < chunk ? (n - off) : chunk;
+        rc = (int)cudaMemcpyAsync(r.pin[slot], d_src + off, cn * sizeof(double), cudaMemcpyDeviceToHost, r.streams[slot]);
+    }
+    for (size_t c = nchunks > (size_t)kStreams ? nchunks - kStreams : 0; c < nchunks && rc == 0; ++c) rc = land(c);
     const int drc = ring_drain(r);
     if (rc == 0) rc = drc;
     if (rc != 0) (void)cudaGetLastError();

@@ -224,3 +224,48 @@ def test_gibbs_step_stays_inside_its_outputs(n, p):
     assert float((psi - want_psi).abs().max()) < 1e-12 * max(1.0, float(want_psi.abs().max()))
     want = X.T @ (om[:, None] * X)
     assert float((G.view(p, p) - want).abs().max()) <= 1e-12 * max(float(want.abs().max()), 1e-300)
+
+
+@pytest.mark.parametrize("n", [1, 4097, (1 << 22) + 3, 3 * (1 << 22), 13_000_007])
+def test_download_fills_exactly_its_destination(n):
+    """pgm_cuda_download (device result -> pageable host array through pinned bounce buffers and several host
+    threads): every element arrives, in order, on both sides of the 2^22-element chunk and of the three-slot
+    ring, and nothing outside [0, n) is written."""
+    torch = _torch()
+    from polyagamma_b200 import _lib
+
+    src = torch.arange(n, dtype=torch.float64, device="cuda") * 0.5 + 1.0
+    host = np.full(n + 2 * 512, -7.0)
+    dst = host[512:512 + n]
+    _lib.check(_lib.lib().pgm_cuda_download(ctypes.c_void_p(dst.ctypes.data), _ptr(src), n, _stream()), "download")
+    assert np.array_equal(dst, src.cpu().numpy())
+    assert (host[:512] == -7.0).all() and (host[512 + n:] == -7.0).all()
+    # a second call reuses the ring
+    src.mul_(-1.0)
+    _lib.check(_lib.lib().pgm_cuda_download(ctypes.c_void_p(dst.ctypes.data), _ptr(src), n, _stream()), "download")
+    assert np.array_equal(dst, src.cpu().numpy())
+
+
+def test_host_results_equal_device_results():
+    """The numpy results of the public functions (which travel through pgm_cuda_download from 2^18 elements on)
+    are the device results, bit for bit."""
+    import polyagamma_b200 as pg
+
+    torch = _torch()
+    x = np.linspace(0.01, 9.0, 700)[:, None]
+    rng = np.random.default_rng(3)
+    h = rng.uniform(0.5, 20.0, 600)[None, :]
+    z = rng.uniform(-8.0, 8.0, 600)[None, :]
+    for f in (pg.polyagamma_pdf, pg.polyagamma_cdf):
+        host = f(x, h, z)
+        dev = f(x, h, z, device="cuda")
+        assert isinstance(host, np.ndarray) and host.shape == (700, 600)
+        assert np.array_equal(host, dev.cpu().numpy(), equal_nan=True)
+    a = pg.random_polyagamma(1.0, 0.5, size=1_000_003, random_state=(5, 6))
+    b = pg.random_polyagamma(1.0, 0.5, size=1_000_003, random_state=(5, 6), device="cuda")
+    assert isinstance(a, np.ndarray) and np.array_equal(a, b.cpu().numpy())
+    hh = rng.uniform(0.2, 90.0, 400_001)
+    zz = rng.uniform(-20.0, 20.0, 400_001)
+    a = pg.random_polyagamma(hh, zz, random_state=(5, 7))
+    b = pg.random_polyagamma(torch.from_numpy(hh).cuda(), torch.from_numpy(zz).cuda(), random_state=(5, 7))
+    assert np.array_equal(a, b.cpu().numpy())
