@@ -13,7 +13,7 @@ import ctypes
 from . import _lib
 from ._api import _device_of, _method_id, _resolve_random_state, _stream_ptr, _torch
 
-__all__ = ["logistic_omega_step"]
+__all__ = ["logistic_omega_step", "sharded_logistic_omega_step", "allreduce_gram"]
 
 
 def logistic_omega_step(X, beta, n_trials=1.0, *, random_state=None, method=None, ref_compat=False,
@@ -57,3 +57,31 @@ def logistic_omega_step(X, beta, n_trials=1.0, *, random_state=None, method=None
             ctypes.c_void_p(psi.data_ptr()) if psi is not None else None, int(first_index), _stream_ptr(dev))
     _lib.check(rc, "pgm_cuda_logistic_omega_step")
     return (gram, omega, psi) if return_psi else (gram, omega)
+
+
+def allreduce_gram(gram, group=None):
+    """Sum the p x p partial Gram matrices of the ranks of ``group`` in place (``torch.distributed``; NCCL for
+    CUDA tensors).  The one exchange of a row-sharded Gibbs sweep: p * p doubles per sweep, whatever n is.  The
+    sum is taken in the collective's order, so it agrees with the single-device matrix to rounding (1e-13
+    relative), not bit for bit; every rank receives the same bits."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(gram, op=dist.ReduceOp.SUM, group=group)
+    return gram
+
+
+def sharded_logistic_omega_step(X_rows, beta, n_trials=1.0, *, row_offset, random_state, group=None, method=None,
+                                ref_compat=False, return_omega=True):
+    """One rank's part of the omega-step when the rows of X are sharded over the ranks of ``group``.
+
+    ``X_rows`` holds rows ``row_offset .. row_offset + len(X_rows)`` of the global design matrix and ``beta`` the
+    full coefficient vector; every rank passes the same ``random_state``.  The rank draws its rows' omegas with
+    ``first_index = row_offset`` -- the Philox streams of the global rows, so the concatenated omegas are
+    bit-identical to the single-device draw -- forms its partial Gram matrix and all-reduces it.  Returns
+    ``(G_global, omega_rows)``."""
+    if random_state is None:
+        raise ValueError("sharded_logistic_omega_step needs an explicit random_state shared by all ranks")
+    gram, omega = logistic_omega_step(X_rows, beta, n_trials, random_state=random_state, method=method,
+                                      ref_compat=ref_compat, return_omega=return_omega, first_index=int(row_offset))
+    return allreduce_gram(gram, group), omega

@@ -78,3 +78,33 @@ def test_omega_step_equals_random_polyagamma(torch):
     assert torch.equal(om3, om4) and torch.equal(G3, G4)
     with pytest.raises(ValueError):
         logistic_omega_step(torch.zeros(4, 65, device="cuda", dtype=torch.float64), torch.zeros(65))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_shards_reproduce_the_single_device_step(torch, world):
+    """Row-sharded sweep (what sharded_logistic_omega_step does per rank, here one shard after the other on
+    one device, and on every visible device in turn): omegas concatenate to the single-call draw bit for bit,
+    the partial Gram matrices add up to the single-call matrix."""
+    from polyagamma_b200.gibbs import logistic_omega_step, sharded_logistic_omega_step
+    from polyagamma_b200.sharding import shard_range
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    n, p = 300_007, 20
+    X = torch.randn(n, p, device="cuda", dtype=torch.float64, generator=g)
+    beta = torch.randn(p, device="cuda", dtype=torch.float64, generator=g) * 0.6
+    nt = torch.randint(1, 4, (n,), device="cuda", generator=g).double()
+    G, om = logistic_omega_step(X, beta, nt, random_state=(3, 1))
+    ndev = torch.cuda.device_count()
+    total = torch.zeros_like(G)
+    for r in range(world):
+        lo, hi = shard_range(n, r, world)
+        dev = torch.device("cuda", r % ndev)
+        # (no process group here: the all-reduce inside is the identity, the sum is taken below)
+        Gr, omr = sharded_logistic_omega_step(X[lo:hi].to(dev), beta.to(dev), nt[lo:hi].to(dev), row_offset=lo,
+                                              random_state=(3, 1))
+        assert torch.equal(omr.to("cuda:0"), om[lo:hi])
+        total += Gr.to("cuda:0")
+    assert float((total - G).abs().max() / G.abs().max()) < 1e-13
+    with pytest.raises(ValueError):
+        sharded_logistic_omega_step(X[:10], beta, 1.0, row_offset=0, random_state=None)

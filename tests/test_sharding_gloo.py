@@ -86,3 +86,46 @@ def test_uneven_three_rank_split(oracle):
     whole = oracle.fill2(2024, 5, h, z)
     got, _ = _run(3)
     assert np.array_equal(got, whole)
+
+
+def _gram_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    from polyagamma_b200.gibbs import allreduce_gram
+    from polyagamma_b200.sharding import shard_range
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    X = torch.from_numpy(rng.normal(size=(1003, 5)))
+    w = torch.from_numpy(rng.uniform(0.1, 2.0, 1003))
+    lo, hi = shard_range(1003, rank, world)
+    part = X[lo:hi].T @ (w[lo:hi, None] * X[lo:hi])
+    total = allreduce_gram(part.clone())
+    if rank == 0:
+        q.put((total.numpy(), (X.T @ (w[:, None] * X)).numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_allreduce_gram_sums_row_shards():
+    """The one collective next to the path: the p x p partial Gram matrices of a row-sharded Gibbs sweep."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gram_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    got, want = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+
+
+def test_allreduce_gram_is_identity_without_a_process_group():
+    sys.path.insert(0, ROOT)
+    from polyagamma_b200.gibbs import allreduce_gram
+
+    g = torch.arange(9.0, dtype=torch.float64).reshape(3, 3)
+    assert torch.equal(allreduce_gram(g.clone()), g)

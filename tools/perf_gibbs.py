@@ -39,10 +39,11 @@ for p, n in ((8, 1 << 27), (16, 1 << 26), (32, 1 << 26), (64, 1 << 25)):
     bytes_x = n * p * 8
     res[f"p={p}"] = {"n": n, "ms": ms, "rows_per_s": n / (ms * 1e-3), "xbeta_ms": xb, "gram_ms": gr,
                      "xbeta_gbs": (bytes_x + 8 * n) / (xb * 1e-3) / 1e9, "gram_gbs": (bytes_x + 8 * n) / (gr * 1e-3) / 1e9,
-                     "gram_tflops": 2.0 * n * p * p / (gr * 1e-3) / 1e12,
+                     # executed: the NB (NB + 1) / 2 tiles of 8 x 8 on or above the diagonal, columns padded to 8 NB
+                     "gram_tflops": 2.0 * n * 64 * (((p + 7) // 8) * ((p + 7) // 8 + 1) // 2) / (gr * 1e-3) / 1e12,
                      "pg_ms": ms - xb - gr}
     print(f"p={p:3d} n={n:.2e}  {n / (ms * 1e-3) / 1e9:6.2f} G rows/s   xbeta {xb:7.2f} ms ({res[f'p={p}']['xbeta_gbs']:6.0f} GB/s)  "
-          f"gram {gr:7.2f} ms ({res[f'p={p}']['gram_gbs']:6.0f} GB/s, {res[f'p={p}']['gram_tflops']:5.1f} TFLOP/s)  PG {ms - xb - gr:7.2f} ms",
+          f"gram {gr:7.2f} ms ({res[f'p={p}']['gram_gbs']:6.0f} GB/s, {res[f'p={p}']['gram_tflops']:5.1f} TFLOP/s executed)  PG {ms - xb - gr:7.2f} ms",
           flush=True)
     del X
     torch.cuda.empty_cache()
