@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -56,12 +57,48 @@ struct Ring {
     cudaStream_t streams[kStreams] = {};
     cudaEvent_t ev_start = nullptr, ev_end = nullptr, ev_join[kStreams] = {};
     double* buf[kStreams][kOperands] = {};
-    double* pin[kStreams] = {};  // pinned bounce buffers of pgm_cuda_download (results on their way to pageable memory)
-    size_t pin_cap = 0;
+    // pinned bounce buffers: [slot][0] results on their way to pageable memory (pgm_cuda_download and fills into
+    // pageable arrays), [slot][1..2] pageable h / z operands on their way to the device
+    double* pin[kStreams][3] = {};
+    size_t pin_cap = 0;  // elements each holds
+    int pin_count = 0;   // buffers per slot that exist (1 after a download, 3 after a bounced fill)
     std::atomic<double> last_ms{0.0};
 };
 Ring g_rings[64];
 thread_local double t_last_ms = 0.0;
+
+void
+ring_free_pinned(Ring& r)
+{
+    for (auto& slot : r.pin)
+        for (auto& p : slot) {
+            if (p) cudaFreeHost(p);
+            p = nullptr;
+        }
+    r.pin_cap = 0;
+    r.pin_count = 0;
+}
+
+// `count` pinned buffers of `need` elements per slot (kept, and grown, across calls)
+int
+ring_prepare_pinned(Ring& r, size_t need, int count)
+{
+    if (r.pin_cap >= need && r.pin_count >= count) return 0;
+    const size_t cap = need > r.pin_cap ? need : r.pin_cap;
+    const int cnt = count > r.pin_count ? count : r.pin_count;
+    ring_free_pinned(r);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < kStreams && e == cudaSuccess; ++i)
+        for (int k = 0; k < cnt && e == cudaSuccess; ++k) e = cudaHostAlloc((void**)&r.pin[i][k], cap * sizeof(double), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        ring_free_pinned(r);
+        (void)cudaGetLastError();
+        return (int)e;
+    }
+    r.pin_cap = cap;
+    r.pin_count = cnt;
+    return 0;
+}
 
 void
 ring_free_buffers(Ring& r)
@@ -72,11 +109,7 @@ ring_free_buffers(Ring& r)
             p = nullptr;
         }
     r.cap = 0;
-    for (auto& p : r.pin) {
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-    }
-    r.pin_cap = 0;
+    ring_free_pinned(r);
 }
 
 void
@@ -164,9 +197,11 @@ struct HostFill {
     double* out;
 };
 
-// queue chunk [off, off + cn) of a fill on ring slot `slot` (no waiting)
+// queue chunk [off, off + cn) of a fill on ring slot `slot` (no waiting); hsrc / zsrc / odst are the chunk's own
+// host arrays (the caller's, or their pinned copies)
 int
-queue_fill_chunk(Ring& r, int slot, const HostFill& f, size_t off, size_t cn, uint64_t first_index)
+queue_fill_chunk(Ring& r, int slot, const HostFill& f, const double* hsrc, const double* zsrc, double* odst, size_t off,
+                 size_t cn, uint64_t first_index)
 {
     cudaStream_t s = r.streams[slot];
     FillArgs a;
@@ -178,7 +213,7 @@ queue_fill_chunk(Ring& r, int slot, const HostFill& f, size_t off, size_t cn, ui
     a.z_stride = 1;
     cudaError_t e;
     if (f.h_stride) {
-        if ((e = cudaMemcpyAsync(r.buf[slot][1], f.h + off, cn * sizeof(double), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+        if ((e = cudaMemcpyAsync(r.buf[slot][1], hsrc, cn * sizeof(double), cudaMemcpyHostToDevice, s)) != cudaSuccess)
             return (int)e;
         a.h = r.buf[slot][1];
     }
@@ -186,7 +221,7 @@ queue_fill_chunk(Ring& r, int slot, const HostFill& f, size_t off, size_t cn, ui
         a.h_scalar = f.h[0];
     }
     if (f.z_stride) {
-        if ((e = cudaMemcpyAsync(r.buf[slot][2], f.z + off, cn * sizeof(double), cudaMemcpyHostToDevice, s)) != cudaSuccess)
+        if ((e = cudaMemcpyAsync(r.buf[slot][2], zsrc, cn * sizeof(double), cudaMemcpyHostToDevice, s)) != cudaSuccess)
             return (int)e;
         a.z = r.buf[slot][2];
     }
@@ -194,33 +229,166 @@ queue_fill_chunk(Ring& r, int slot, const HostFill& f, size_t off, size_t cn, ui
         a.z_scalar = f.z[0];
     }
     if (int rc = pgm::launch_fill(a, cn, f.method, s)) return rc;
-    return (int)cudaMemcpyAsync(f.out + off, r.buf[slot][3], cn * sizeof(double), cudaMemcpyDeviceToHost, s);
+    return (int)cudaMemcpyAsync(odst, r.buf[slot][3], cn * sizeof(double), cudaMemcpyDeviceToHost, s);
 }
 
-// memcpy by several host threads: the destination is usually a freshly allocated array, and its first touch
-// (page faults) is what a single thread cannot do faster than ~2 GB/s
+// memcpy by several host threads.  The destination of a result is usually a freshly allocated array whose first
+// touch (page faults) one thread cannot do faster than ~2 GB/s, and a single thread's memcpy between pageable
+// and pinned memory is well below what the host link carries.  The workers are started once per process and
+// sleep between calls; callers (one per device ring) take turns.
+class CopyPool {
+  public:
+    void copy(double* dst, const double* src, size_t n)
+    {
+        constexpr size_t kMinPerThread = size_t(1) << 17;  // 1 MiB
+        std::lock_guard<std::mutex> turn(turn_);
+        start_workers();
+        size_t parts = workers_.size() + 1;
+        if (n / kMinPerThread < parts) parts = n / kMinPerThread;
+        if (parts <= 1) {
+            memcpy(dst, src, n * sizeof(double));
+            return;
+        }
+        const size_t per = ((n + parts - 1) / parts + 511) & ~size_t(511);  // (page-sized pieces)
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = dst, src_ = src, n_ = n, per_ = per;
+            next_ = 1;  // piece 0 is the caller's
+            pending_ = 0;
+            for (size_t lo = per; lo < n; lo += per) ++pending_;
+            ++generation_;
+        }
+        cv_.notify_all();
+        memcpy(dst, src, (per < n ? per : n) * sizeof(double));
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+
+  private:
+    void start_workers()
+    {
+        if (!workers_.empty() || started_) return;
+        started_ = true;
+        unsigned hw = std::thread::hardware_concurrency();
+        const unsigned nt = hw >= 16 ? 7 : (hw >= 4 ? hw / 2 - 1 : 0);
+        for (unsigned i = 0; i < nt; ++i) workers_.emplace_back([this] { run(); });
+    }
+    void run()
+    {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu_);
+        for (;;) {
+            cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            for (;;) {
+                const size_t lo = next_ * per_;
+                if (lo >= n_) break;
+                ++next_;
+                const size_t cnt = (n_ - lo) < per_ ? (n_ - lo) : per_;
+                double* d = dst_ + lo;
+                const double* sp = src_ + lo;
+                lk.unlock();
+                memcpy(d, sp, cnt * sizeof(double));
+                lk.lock();
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::mutex turn_, mu_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> workers_;
+    bool started_ = false, stop_ = false;
+    uint64_t generation_ = 0;
+    double* dst_ = nullptr;
+    const double* src_ = nullptr;
+    size_t n_ = 0, per_ = 0, next_ = 0, pending_ = 0;
+};
+CopyPool g_copy_pool;
+
 void
 parallel_memcpy(double* dst, const double* src, size_t n)
 {
-    constexpr size_t kMinPerThread = size_t(1) << 18;  // 2 MiB
-    unsigned hw = std::thread::hardware_concurrency();
-    size_t nt = hw >= 16 ? 8 : (hw >= 4 ? hw / 2 : 1);
-    if (n / kMinPerThread < nt) nt = n / kMinPerThread;
-    if (nt <= 1) {
-        memcpy(dst, src, n * sizeof(double));
-        return;
+    g_copy_pool.copy(dst, src, n);
+}
+
+// is p ordinary (pageable) host memory?  Pinned / registered / managed memory can be the end point of an
+// asynchronous copy at link speed; pageable memory is staged by the driver, synchronously, by one thread.
+bool
+is_pageable(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
     }
-    // split on page boundaries of the destination
-    const size_t per = ((n + nt - 1) / nt + 511) & ~size_t(511);
-    std::vector<std::thread> pool;
-    for (size_t t = 1; t < nt; ++t) {
-        const size_t lo = t * per;
-        if (lo >= n) break;
-        const size_t cnt = (n - lo) < per ? (n - lo) : per;
-        pool.emplace_back([=] { memcpy(dst + lo, src + lo, cnt * sizeof(double)); });
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// A fill whose operands or result live in PAGEABLE host memory (plain numpy arrays: what a caller of the
+// reference has).  Handing such pointers to cudaMemcpyAsync makes the driver stage them itself, synchronously
+// and with one thread (~13 GB/s over all three arrays on the bench box).  Here the chunks go through the ring's
+// pinned buffers instead: the copy pool moves chunk c of h and z in, the device works on it asynchronously, and
+// the results of chunk c - 3 are moved out while it does.
+int
+bounced_fill(Ring& r, const HostFill& f, size_t n, uint64_t first_index)
+{
+    constexpr size_t kBounceChunk = size_t(1) << 21;  // 16 MiB per buffer, nine buffers
+    const size_t chunk = n < kBounceChunk ? n : kBounceChunk;
+    int rc = ring_prepare(r, chunk, kOperands);
+    if (rc == 0) rc = ring_prepare_pinned(r, chunk, 3);
+    if (rc != 0) return rc;
+    cudaEventRecord(r.ev_start, r.streams[0]);
+    for (int k = 1; k < kStreams; ++k) cudaStreamWaitEvent(r.streams[k], r.ev_start, 0);
+    const size_t nchunks = (n + chunk - 1) / chunk;
+    auto span = [&](size_t c, size_t& off, size_t& cn) {
+        off = c * chunk;
+        cn = (n - off) < chunk ? (n - off) : chunk;
+    };
+    auto land = [&](size_t c) {
+        const int slot = (int)(c % kStreams);
+        const cudaError_t es = cudaStreamSynchronize(r.streams[slot]);
+        if (es != cudaSuccess) return (int)es;
+        size_t off, cn;
+        span(c, off, cn);
+        parallel_memcpy(f.out + off, r.pin[slot][0], cn);
+        return 0;
+    };
+    for (size_t c = 0; c < nchunks && rc == 0; ++c) {
+        const int slot = (int)(c % kStreams);
+        if (c >= (size_t)kStreams && (rc = land(c - kStreams)) != 0) break;
+        size_t off, cn;
+        span(c, off, cn);
+        if (f.h_stride) parallel_memcpy(r.pin[slot][1], f.h + off, cn);
+        if (f.z_stride) parallel_memcpy(r.pin[slot][2], f.z + off, cn);
+        rc = queue_fill_chunk(r, slot, f, r.pin[slot][1], r.pin[slot][2], r.pin[slot][0], off, cn, first_index);
     }
-    memcpy(dst, src, (per < n ? per : n) * sizeof(double));
-    for (auto& th : pool) th.join();
+    for (size_t c = nchunks > (size_t)kStreams ? nchunks - kStreams : 0; c < nchunks && rc == 0; ++c) rc = land(c);
+    if (rc == 0) {
+        for (int k = 1; k < kStreams; ++k) {
+            cudaEventRecord(r.ev_join[k], r.streams[k]);
+            cudaStreamWaitEvent(r.streams[0], r.ev_join[k], 0);
+        }
+        cudaEventRecord(r.ev_end, r.streams[0]);
+    }
+    const int drc = ring_drain(r);
+    if (rc == 0) rc = drc;
+    float ms = 0.f;
+    if (rc == 0 && cudaEventElapsedTime(&ms, r.ev_start, r.ev_end) == cudaSuccess) {
+        r.last_ms.store(ms);
+        t_last_ms = ms;
+    }
+    if (rc != 0) (void)cudaGetLastError();
+    return rc;
 }
 
 // ---- one draw / a handful of points: mapped pinned memory, one launch --------------------------------------
@@ -294,6 +462,15 @@ pgm_cuda_random_polyagamma_fill2_host_multi(uint64_t seed, uint64_t offset, cons
             if (devices[i] == devices[j] || devices[i] < 0) return PGM_CUDA_EINVAL;
     if ((size_t)ndevices > n) ndevices = (int)n;
     DeviceGuard guard(-1);
+    // pageable arrays (one device, enough elements that the copies matter): bounce them through pinned memory
+    if (ndevices == 1 && n >= (size_t(1) << 16) &&
+        ((h_stride && is_pageable(h)) || (z_stride && is_pageable(z)) || is_pageable(out))) {
+        if (cudaSetDevice(devices[0]) != cudaSuccess) return (int)cudaGetLastError();
+        Ring& r = g_rings[devices[0] & 63];
+        std::lock_guard<std::mutex> lock(r.mu);
+        const HostFill fb{seed, offset, h, z, h_stride, z_stride, method, out};
+        return bounced_fill(r, fb, n, first_index);
+    }
 
     // contiguous shards of the index range, one per device (the partition of polyagamma_b200/sharding.py);
     // a shard's elements keep their global Philox indices, so the result does not depend on ndevices
@@ -345,7 +522,8 @@ pgm_cuda_random_polyagamma_fill2_host_multi(uint64_t seed, uint64_t offset, cons
                 rc = (int)cudaGetLastError();
                 break;
             }
-            rc = queue_fill_chunk(*s.ring, s.chunks_queued % kStreams, f, s.next, cn, first_index);
+            rc = queue_fill_chunk(*s.ring, s.chunks_queued % kStreams, f, f.h + (f.h_stride ? s.next : 0),
+                                  f.z + (f.z_stride ? s.next : 0), f.out + s.next, s.next, cn, first_index);
             s.next += cn;
             s.chunks_queued += 1;
             more = more || s.next < s.hi;
@@ -489,24 +667,8 @@ pgm_cuda_download(double* dst, const double* d_src, size_t n, void* stream)
     if (rc != 0) return rc;
     constexpr size_t kPinChunk = size_t(1) << 22;  // 32 MiB per bounce buffer
     const size_t chunk = n < kPinChunk ? n : kPinChunk;
+    if ((rc = ring_prepare_pinned(r, chunk, 1)) != 0) return rc;
     cudaError_t e = cudaSuccess;
-    if (r.pin_cap < chunk) {
-        for (auto& p : r.pin) {
-            if (p) cudaFreeHost(p);
-            p = nullptr;
-        }
-        r.pin_cap = 0;
-        for (int i = 0; i < kStreams && e == cudaSuccess; ++i) e = cudaHostAlloc((void**)&r.pin[i], chunk * sizeof(double), cudaHostAllocDefault);
-        if (e != cudaSuccess) {
-            for (auto& p : r.pin) {
-                if (p) cudaFreeHost(p);
-                p = nullptr;
-            }
-            (void)cudaGetLastError();
-            return (int)e;
-        }
-        r.pin_cap = chunk;
-    }
     // the producer's stream has to be done with d_src before the ring's streams read it
     if ((e = cudaEventRecord(r.ev_join[0], (cudaStream_t)stream)) != cudaSuccess) return (int)e;
     for (int i = 0; i < kStreams; ++i) cudaStreamWaitEvent(r.streams[i], r.ev_join[0], 0);
@@ -516,7 +678,7 @@ pgm_cuda_download(double* dst, const double* d_src, size_t n, void* stream)
         const cudaError_t es = cudaStreamSynchronize(r.streams[slot]);
         if (es != cudaSuccess) return (int)es;
         const size_t off = c * chunk, cn = (n - off) < chunk ? (n - off) : chunk;
-        parallel_memcpy(dst + off, r.pin[slot], cn);
+        parallel_memcpy(dst + off, r.pin[slot][0], cn);
         return 0;
     };
     for (size_t c = 0; c < nchunks && rc == 0; ++c) {
@@ -524,7 +686,7 @@ pgm_cuda_download(double* dst, const double* d_src, size_t n, void* stream)
         if (c >= (size_t)kStreams) rc = land(c - kStreams);
         if (rc != 0) break;
         const size_t off = c * chunk, cn = (n - off) < chunk ? (n - off) : chunk;
-        rc = (int)cudaMemcpyAsync(r.pin[slot], d_src + off, cn * sizeof(double), cudaMemcpyDeviceToHost, r.streams[slot]);
+        rc = (int)cudaMemcpyAsync(r.pin[slot][0], d_src + off, cn * sizeof(double), cudaMemcpyDeviceToHost, r.streams[slot]);
     }
     for (size_t c = nchunks > (size_t)kStreams ? nchunks - kStreams : 0; c < nchunks && rc == 0; ++c) rc = land(c);
     const int drc = ring_drain(r);

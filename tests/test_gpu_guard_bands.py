@@ -269,3 +269,37 @@ def test_host_results_equal_device_results():
     a = pg.random_polyagamma(hh, zz, random_state=(5, 7))
     b = pg.random_polyagamma(torch.from_numpy(hh).cuda(), torch.from_numpy(zz).cuda(), random_state=(5, 7))
     assert np.array_equal(a, b.cpu().numpy())
+
+
+@pytest.mark.parametrize("n", [65_536, (1 << 21) - 1, (1 << 21) + 1, 3 * (1 << 21) + 5, 7 * (1 << 21) + 1])
+@pytest.mark.parametrize("scalar_h", [False, True])
+def test_pageable_host_fill_is_bounced_correctly(n, scalar_h):
+    """fill2_host with plain numpy (pageable) arrays goes through pinned bounce buffers in 2^21-element chunks
+    on a three-slot ring: every element equals the device-resident call's, on both sides of the chunk size and
+    of the ring length, and the sentinels around `out` stay."""
+    torch = _torch()
+    from polyagamma_b200 import _lib
+
+    rng = np.random.default_rng(n % 1000)
+    h = np.array([2.5]) if scalar_h else rng.uniform(0.2, 150.0, n)
+    z = rng.uniform(-30.0, 30.0, n)
+    host = np.full(n + 2 * 512, -7.0)
+    out = host[512:512 + n]
+    rc = _lib.lib().pgm_cuda_random_polyagamma_fill2_host(31, 4, h.ctypes.data, 0 if scalar_h else 1, z.ctypes.data, 1,
+                                                          _lib.HYBRID, n, out.ctypes.data, 17, -1)
+    _lib.check(rc, "fill2_host")
+    assert (host[:512] == -7.0).all() and (host[512 + n:] == -7.0).all()
+    hd = torch.full((n,), 2.5, dtype=torch.float64, device="cuda") if scalar_h else torch.from_numpy(h).cuda()
+    zd = torch.from_numpy(z).cuda()
+    ref = torch.empty(n, dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().pgm_cuda_random_polyagamma_fill2(31, 4, _ptr(hd), _ptr(zd), _lib.HYBRID, n, _ptr(ref), 17, _stream()),
+               "fill2")
+    torch.cuda.synchronize()
+    assert np.array_equal(out, ref.cpu().numpy())
+    # pinned arrays take the direct path and give the same bits
+    hp, zp = torch.from_numpy(h).pin_memory(), torch.from_numpy(z).pin_memory()
+    op = torch.empty(n, dtype=torch.float64).pin_memory()
+    rc = _lib.lib().pgm_cuda_random_polyagamma_fill2_host(31, 4, hp.data_ptr(), 0 if scalar_h else 1, zp.data_ptr(), 1,
+                                                          _lib.HYBRID, n, op.data_ptr(), 17, -1)
+    _lib.check(rc, "fill2_host pinned")
+    assert np.array_equal(op.numpy(), out)
