@@ -91,7 +91,9 @@ int pgm_cuda_random_polyagamma_fill2_strided(uint64_t seed, uint64_t offset, con
 /* Host-buffer form of fill2 (the reference's calling convention: all pointers are host memory,
  * include/pgm_random.h:72-74).  h_stride / z_stride are 1 (array of n) or 0 (scalar broadcast).  Copies are
  * chunked and overlapped with the kernels on a ring of three internal streams of `device` (< 0: the current
- * one); pinned (page-locked) buffers give full PCIe speed.  Blocks until `out` is complete; on failure it
+ * one); pinned (page-locked) buffers give the full speed of the host link, pageable ones (an ordinary malloc or
+ * numpy array) of 2^16 elements or more are bounced through pinned buffers of the ring (3 x 3 x 16 MiB, kept until
+ * pgm_cuda_release_scratch) by a small pool of host threads.  Blocks until `out` is complete; on failure it
  * still does not return before every copy it queued has finished.  The ring's device staging (3 streams x 4
  * operands x the chunk size, at most 64 MiB each, sized by the largest call so far) stays allocated until
  * pgm_cuda_release_scratch.  Calls on different devices run concurrently; calls on one device take turns. */
