@@ -137,6 +137,39 @@ static __constant__ double c_cos[6] = {4.16666666666666019037e-02,  -1.388888888
 constexpr double kLn2Hi = 6.93147180369123816490e-01;
 constexpr double kLn2Lo = 1.90821492927058770002e-10;
 
+// PGM_TABLE_MATH (default 1): fm::exp by a table of 2^(j/64) and a degree-5 polynomial, fm::cos2pi by ONE
+// polynomial whose coefficients (sine or cosine kernel) are loaded per lane -- both read their tables through
+// the read-only path (L1 resident: 512 + 96 bytes).  An FP64 instruction cannot take a constant-bank operand
+// here, so every polynomial coefficient costs a load besides its FMA; halving the polynomials pays twice.
+// 0 makes them the table-free exp_poly / cos2pi_poly everywhere.
+#ifndef PGM_TABLE_MATH
+#define PGM_TABLE_MATH 1
+#endif
+// 2^(j/64), correctly rounded (mpmath)
+static __device__ const double g_exp2_64[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+// [0] the cosine kernel's coefficients, [1] the sine kernel's (the values of c_cos / c_sin), in pairs
+static __device__ const double2 g_sincos_coef[2][3] = {
+    {{4.16666666666666019037e-02, -1.38888888888741095749e-03}, {2.48015872894767294178e-05, -2.75573143513906633035e-07},
+     {2.08757232129817482790e-09, -1.13596475577881948265e-11}},
+    {{-1.66666666666666324348e-01, 8.33333333332248946124e-03}, {-1.98412698298579493134e-04, 2.75573137070700676789e-06},
+     {-2.50507602534068634195e-08, 1.58969099521155010221e-10}}};
+
 // The libdevice fallbacks for arguments outside the lean paths' domain.  They are INLINED on purpose.  Out of
 // line (__noinline__: a few KB less never-executed code between the hot instructions of every call site) the
 // persistent sampling kernels hung intermittently -- sample_kernel<Alternate> on chunked elements, one warp
@@ -235,9 +268,12 @@ log(double x)
 }
 
 // e^x for x <= 700; x < -707 flushes to 0 (the samplers never need denormal results), huge or NaN arguments go
-// to libdevice.
+// to libdevice.  Two forms, both within 2 ulp: `exp` reads 2^(j/64) from a table and needs a degree-5
+// polynomial; `exp_poly` is table-free (degree 13 on |r| <= ln2/2).  Which one is faster depends on the kernel:
+// the list kernels and the densities gain 2-4 % from the table, the tile kernel (64 registers, 4 blocks per SM)
+// loses 2.5 % to the extra load, so its two methods (normal approximation, left-only saddle) call exp_poly.
 __device__ __forceinline__ double
-exp(double x)
+exp_poly(double x)
 {
     if (!(x <= 700.0)) return slow_exp(x);  // huge or NaN
     if (x < -707.0) return 0.0;
@@ -254,9 +290,35 @@ exp(double x)
     return __longlong_as_double(__double_as_longlong(p) + ((long long)n << 52));
 }
 
-// cos(2 pi u) for u in [0, 1]: quadrant from round(4u), sine/cosine kernels on [-pi/4, pi/4]
 __device__ __forceinline__ double
-cos2pi(double u)
+exp(double x)
+{
+#if PGM_TABLE_MATH
+    if (!(x <= 700.0)) return slow_exp(x);  // huge or NaN
+    if (x < -707.0) return 0.0;
+    // k = round(64 x / ln 2) = 64 n + j;  e^x = 2^n 2^(j/64) e^r,  |r| <= ln2/128: degree 5 is below 4e-17
+    const double t = fma(x, 92.332482616893656, 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double dn = t - 6755399441055744.0;
+    double r = fma(dn, -kLn2Hi * 0.015625, x);  // (dn kLn2Hi / 64 is exact: 33 + 17 significant bits)
+    r = fma(dn, -kLn2Lo * 0.015625, r);
+    const double T = __ldg(&g_exp2_64[k & 63]);
+    double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q * r, r, r);  // e^r - 1
+    const double v = fma(T, q, T);
+    return __longlong_as_double(__double_as_longlong(v) + ((long long)(k >> 6) << 52));
+#else
+    return exp_poly(x);
+#endif
+}
+
+// cos(2 pi u) for u in [0, 1]: quadrant from round(4u), sine/cosine kernels on [-pi/4, pi/4].  `cos2pi` runs ONE
+// Horner chain on the coefficients of the lane's quadrant (loaded per lane), `cos2pi_poly` both fixed
+// polynomials and a select; same values to 1e-16, same trade as exp / exp_poly.
+__device__ __forceinline__ double
+cos2pi_poly(double u)
 {
     const double v = 4.0 * u;
     const double t = v + 6755399441055744.0;
@@ -274,6 +336,34 @@ cos2pi(double u)
     cs = fma(y2 * y2, cs, fma(-0.5, y2, 1.0));
     const double val = (q & 1) ? sn : cs;
     return ((q + 1) & 2) ? -val : val;  // q: 0 -> cos, 1 -> -sin, 2 -> -cos, 3 -> sin, 4 -> cos
+}
+
+__device__ __forceinline__ double
+cos2pi(double u)
+{
+#if PGM_TABLE_MATH
+    const double v = 4.0 * u;
+    const double t = v + 6755399441055744.0;
+    const int q = __double2loint(t);
+    const double r = v - (t - 6755399441055744.0);
+    const double y = r * 1.5707963267948966;
+    const double y2 = y * y;
+    // sine kernel  y + y y2 S(y2)  or cosine kernel  1 - y2/2 + y2 y2 C(y2)
+    const bool odd = (q & 1) != 0;
+    const double2* c = g_sincos_coef[odd ? 1 : 0];
+    const double2 c01 = __ldg(c), c23 = __ldg(c + 1), c45 = __ldg(c + 2);
+    double p = fma(c45.y, y2, c45.x);
+    p = fma(p, y2, c23.y);
+    p = fma(p, y2, c23.x);
+    p = fma(p, y2, c01.y);
+    p = fma(p, y2, c01.x);
+    const double A = odd ? y : fma(-0.5, y2, 1.0);
+    const double B = (odd ? y : y2) * y2;
+    const double val = fma(B, p, A);
+    return ((q + 1) & 2) ? -val : val;
+#else
+    return cos2pi_poly(u);
+#endif
 }
 
 // sin and cos of 2 pi u together (Box-Muller pairs)

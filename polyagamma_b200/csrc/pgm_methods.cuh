@@ -867,7 +867,7 @@ struct SaddleT {
         // (below 1e-100 every quantity here equals its z = 0 value in double precision; the cut keeps
         // the MUFU-seeded reciprocals on normal numbers)
         if (zz > 1e-100) {
-            const double e = exp(-2.0 * zz);
+            const double e = fm::exp_poly(-2.0 * zz);
             xl = fm::div(1.0 - e, (1.0 + e) * zz);  // tanh(zz) / zz
             half_z2 = 0.5 * zz * zz;
             l2cz = zz + log(1.0 + e);  // (absolute accuracy is what counts here: no log1p needed)
@@ -953,7 +953,7 @@ struct SaddleT {
             const double mu = p.xl, mu2 = p.xl * p.xl;
             do {  // IG(mu = xl, lambda = h) | x < xc, Michael-Schucany-Haas; only the normal's square is needed
                 const double L = -fm::log_pn(r.uniform_oc());
-                const double c = fm::cos2pi(r.uniform_co());
+                const double c = fm::cos2pi_poly(r.uniform_co());
                 const double y2 = 2.0 * L * c * c;
                 double w = mu + 0.5 * mu2 * y2 * p.inv_h;
                 x = mu2 * fm::rcp(w + fm::sqrt_nn(w * w - mu2));
@@ -1006,7 +1006,7 @@ normal_approx_sample(R& r, double h, double z)
     else {
         // tanh(a/2) = (1 - e)/(1 + e) and sech^2(a/2) = 4 e / (1 + e)^2 with e = e^{-a}; one
         // reciprocal rinv = 1 / ((1 + e) a) serves the mean and the variance
-        const double e = exp(-a);
+        const double e = fm::exp_poly(-a);  // (the tile kernel's two methods stay table-free: see fm::exp)
         const double ope = 1.0 + e;
         const double rinv = fm::rcp(ope * a);
         mean = 0.5 * h * (1.0 - e) * rinv;
@@ -1026,7 +1026,7 @@ normal_approx_sample(R& r, double h, double z)
     // mean + N sqrt(var) with the Box-Muller radius folded into one square root
     const double u1 = r.uniform_oc();
     const double u2 = r.uniform_co();
-    return mean + fm::sqrt_nn(-2.0 * var * fm::log_pn(u1)) * fm::cos2pi(u2);
+    return mean + fm::sqrt_nn(-2.0 * var * fm::log_pn(u1)) * fm::cos2pi_poly(u2);
 }
 
 // random_polyagamma_gamma_conv (src/pgm_random.c:79-97): 200 Marsaglia-Tsang gammas

@@ -1617,6 +1617,8 @@ test_math_kernel(int which, const double* __restrict__ in, size_t n, double* __r
             case 6: fm::sincos2pi(x, y, t); break;
             case 7: fm::sincos2pi(x, t, y); break;
             case 9: y = pgm_lgamma(x); break;
+            case 12: y = fm::exp_poly(x); break;
+            case 13: y = fm::cos2pi_poly(x); break;
             case 10: y = fm::erfcx_pos(x); break;
             case 11: y = fm::erfcx_pos(x) * fm::exp_neg_sq(x); break;  // erfc(x), x >= 0, as the cdf kernels form it
             case 20: saddle::lookup<true>(x, y, t); break;               // Gr(x), tabulated
