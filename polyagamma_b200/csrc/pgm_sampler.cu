@@ -231,21 +231,30 @@ list_slot(int bucket)
 {
     switch (bucket) {
         case kBAlternate: return 0;
-        case kBSaddleFull: return 1;
-        case kBAlternateLeft: return 2;
-        case kBDevroye: return 3;
-        case kBDevroyeMSH: return 4;
+        case kBAlternateLeft: return 1;
+        case kBDevroye: return 2;
+        case kBDevroyeMSH: return 3;
+        case kBSaddleFull: return 4;
         default: return -1;  // drawn in the tile
     }
 }
 constexpr int kNumListSlots = 5;
+// An element is in one list at most, but any list can hold the whole pass.  Two slots share a region of
+// `stride` entries: the even one grows from its front, the odd one from its back, so five worst-case lists
+// take three regions (60 instead of 100 bytes per element of the pass).
+constexpr int kNumListRegions = (kNumListSlots + 1) / 2;
 
 struct ElemLists {
-    uint32_t* idx;  // slot s: idx + s * stride, h + s * stride, z + s * stride
+    uint32_t* idx;  // entry p of slot s at list_entry(s, stride, p) of each array
     double* h;
     double* z;
     uint32_t stride;
 };
+__host__ __device__ __forceinline__ size_t
+list_entry(int slot, uint32_t stride, uint32_t p)
+{
+    return (size_t)(slot >> 1) * stride + ((slot & 1) ? stride - 1u - p : p);
+}
 
 // ---------------------------------------------------------------------------------------
 // work description shared by the per-method kernels
@@ -262,6 +271,7 @@ struct Bucket {
     uint32_t count_imm;
     double* params;  // record storage (M::kFields doubles per element, structure of arrays)
     int uniform;     // 1: one record (position 0) serves every element (scalar h and z)
+    int dir = 1;     // list mode: entry p is at idx[dir * p] (-1: a list that grows from the back of its region)
 };
 
 struct BucketView {
@@ -288,9 +298,10 @@ __device__ __forceinline__ void
 bucket_operands(const FillArgs& a, const Bucket& b, uint32_t pos, uint32_t& e, double& h, double& z)
 {
     if (b.idx) {
-        e = b.idx[pos];
-        h = b.lh[pos];
-        z = b.lz[pos];
+        const ptrdiff_t o = (ptrdiff_t)b.dir * (ptrdiff_t)pos;
+        e = b.idx[o];
+        h = b.lh[o];
+        z = b.lz[o];
     }
     else {
         e = pos;
@@ -688,13 +699,14 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
             const uint32_t c = cnt[q];
             if (c == 0) continue;  // block-uniform
             const uint32_t off = S.off[q];
-            const size_t dst = (size_t)slot * el.stride + S.gbase[q];
+            const uint32_t first = S.gbase[q];
 #pragma unroll 1
             for (uint32_t i = tid; i < c; i += kTileThreads) {
                 const uint32_t e = S.list[off + i];
-                el.idx[dst + i] = tile0 + e;
-                el.h[dst + i] = S.hout[e];
-                el.z[dst + i] = S.z[e];
+                const size_t dst = list_entry(slot, el.stride, first + i);
+                el.idx[dst] = tile0 + e;
+                el.h[dst] = S.hout[e];
+                el.z[dst] = S.z[e];
             }
         }
         // ---- 5. the tile's outputs ----
@@ -813,7 +825,7 @@ sample_kernel(FillArgs a, Bucket b, uint32_t* __restrict__ counter)
                         }
                     }
                     else {
-                        g = a.base + (v.idx ? v.idx[pos] : pos);
+                        g = a.base + (v.idx ? v.idx[(ptrdiff_t)b.dir * (ptrdiff_t)pos] : pos);
                         RecView rec{v.recs, v.stride, b.uniform ? 0u : pos};
                         double r0 = rec[0];
                         if (r0 == r0) {  // NaN record: invalid h, already written by setup_kernel
@@ -958,7 +970,7 @@ drain_kernel(FillArgs a, ElemLists el, const uint32_t* __restrict__ ctl)
     const uint32_t k0 = a.key.k0, k1 = a.key.k1;
     // end of each list slot's range in the common index space
     uint32_t end[kNumListSlots];
-    const int bucket_of_slot[kNumListSlots] = {kBAlternate, kBSaddleFull, kBAlternateLeft, kBDevroye, kBDevroyeMSH};
+    const int bucket_of_slot[kNumListSlots] = {kBAlternate, kBAlternateLeft, kBDevroye, kBDevroyeMSH, kBSaddleFull};
     uint32_t total = 0;
 #pragma unroll
     for (int sl = 0; sl < kNumListSlots; ++sl) {
@@ -976,17 +988,17 @@ drain_kernel(FillArgs a, ElemLists el, const uint32_t* __restrict__ ctl)
                 first = end[j];
             }
         }
-        const size_t o = (size_t)sl * el.stride + (p - first);
+        const size_t o = list_entry(sl, el.stride, p - first);
         const uint32_t idx = el.idx[o];
         const double h = el.h[o], z = el.z[o];
         const uint64_t index = a.first_index + a.base + idx;
         double v;
         switch (sl) {  // (list_slot())
             case 0: v = run_one<Alternate>(k0, k1, index, h, z, compat); break;
-            case 1: v = run_one<SaddleFull>(k0, k1, index, h, z, compat); break;
-            case 2: v = run_one<AlternateLeft>(k0, k1, index, h, z, compat); break;
-            case 3: v = run_one<DevroyeT<kDevroyePair>>(k0, k1, index, h, z, compat); break;
-            default: v = run_one<DevroyeT<kDevroyeMSH>>(k0, k1, index, h, z, compat); break;
+            case 1: v = run_one<AlternateLeft>(k0, k1, index, h, z, compat); break;
+            case 2: v = run_one<DevroyeT<kDevroyePair>>(k0, k1, index, h, z, compat); break;
+            case 3: v = run_one<DevroyeT<kDevroyeMSH>>(k0, k1, index, h, z, compat); break;
+            default: v = run_one<SaddleFull>(k0, k1, index, h, z, compat); break;
         }
         a.out[a.base + idx] = v;
     }
@@ -1118,6 +1130,20 @@ int
 device_init()
 {
     return device_info().init_rc;
+}
+
+// bytes the private pool holds right now (in use or cached for reuse)
+static size_t
+scratch_held_bytes()
+{
+    DeviceInfo d = device_info();
+    if (d.init_rc != 0) return 0;
+    uint64_t v = 0;
+    if (cudaMemPoolGetAttribute(d.pool, cudaMemPoolAttrReservedMemCurrent, &v) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return (size_t)v;
 }
 
 int
@@ -1281,7 +1307,7 @@ mid_max()
 // on cfg4 -- those kernels are divergence-bound, not tail-bound, and what is left for the forced drain after the
 // last pass has nothing to overlap with.)
 #ifndef PGM_CHUNK_LOG2_MAX
-#define PGM_CHUNK_LOG2_MAX 25
+#define PGM_CHUNK_LOG2_MAX 27
 #endif
 constexpr int kChunkLog2Min = 20, kChunkLog2Max = PGM_CHUNK_LOG2_MAX;
 
@@ -1312,13 +1338,30 @@ fill_arrays(const DeviceInfo& d, FillArgs a, uint64_t n, int m, cudaStream_t s)
     const size_t ctl_bytes = align256(kCtlWords * sizeof(uint32_t));
     constexpr int kRecFields = Alternate::kFields + SaddleFull::kFields;
     char* ws = nullptr;
+    // Passes above 2^25 elements are worth 4 % on a mixed fill (the divergent buckets' kernels of a pass are
+    // latency bound: fewer, longer ones), but their worst-case lists and records are 232 bytes per element of the
+    // pass: take them only while the scratch stays below a third of the memory that is free right now.
+    if (lg > 25 && !env_chunk_log2()) {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+            (void)cudaGetLastError();
+            free_b = 0;
+        }
+        const size_t held = scratch_held_bytes();  // (what the pool already holds is reused, not taken again)
+        while (lg > 25) {
+            const uint64_t c = (n < (1ull << lg)) ? n : (1ull << lg);
+            const size_t want = (size_t)c * ((n > c ? 2 : 1) * kNumListRegions * 20 + kRecFields * 8);
+            if (want <= held || want - held <= free_b / 3) break;
+            --lg;
+        }
+    }
     for (;;) {
         chunk = 1ull << lg;
         mid = mid_ok && n <= chunk;
         const uint64_t cmax = n < chunk ? n : chunk;
         nsets = (n > chunk && !no_overlap && any_buckets) ? 2 : 1;
         cap = (uint32_t)((cmax + 63) & ~uint64_t(63));
-        list_bytes = any_buckets ? align256((size_t)cap * kNumListSlots * (sizeof(uint32_t) + 2 * sizeof(double))) : 0;
+        list_bytes = any_buckets ? align256((size_t)cap * kNumListRegions * (sizeof(uint32_t) + 2 * sizeof(double))) : 0;
         rec_bytes = (any_buckets && !mid) ? align256((size_t)cap * kRecFields * sizeof(double)) : 0;
         err = (cudaError_t)scratch_alloc((void**)&ws, nsets * (ctl_bytes + list_bytes) + rec_bytes, s);
         if (err == cudaSuccess) break;
@@ -1335,8 +1378,8 @@ fill_arrays(const DeviceInfo& d, FillArgs a, uint64_t n, int m, cudaStream_t s)
         char* base = ws + (size_t)nsets * ctl_bytes + (size_t)i * list_bytes;
         // h and z first (8-byte aligned whatever the capacity), then the indices
         set[i].el.h = (double*)base;
-        set[i].el.z = set[i].el.h + (size_t)cap * kNumListSlots;
-        set[i].el.idx = (uint32_t*)(set[i].el.z + (size_t)cap * kNumListSlots);
+        set[i].el.z = set[i].el.h + (size_t)cap * kNumListRegions;
+        set[i].el.idx = (uint32_t*)(set[i].el.z + (size_t)cap * kNumListRegions);
         set[i].el.stride = cap;
     }
     if (nsets == 1) set[1] = set[0];
@@ -1368,8 +1411,9 @@ fill_arrays(const DeviceInfo& d, FillArgs a, uint64_t n, int m, cudaStream_t s)
     // there, so the host never waits for a count (an empty bucket costs one near-empty launch).
     auto bucket_pass = [&](const FillArgs& ap, const ListSet& ls, cudaStream_t s1, cudaStream_t s2) {
         auto bucket = [&](int q, double* recs) {
-            const size_t o = (size_t)list_slot(q) * cap;
-            return Bucket{ls.el.idx + o, ls.el.h + o, ls.el.z + o, ls.ctl, q, 0, recs, 0};
+            const int slot = list_slot(q);
+            const size_t o = list_entry(slot, cap, 0);  // entry 0: the front of the slot's region, or its back
+            return Bucket{ls.el.idx + o, ls.el.h + o, ls.el.z + o, ls.ctl, q, 0, recs, 0, (slot & 1) ? -1 : 1};
         };
         if (m == kHybrid || m == kSaddle)
             launch_method<SaddleFull>(d, 2, ap, bucket(kBSaddleFull, rec_full), cap, ls.ctl + kCtlWork + kBSaddleFull, s2);
