@@ -67,7 +67,7 @@ SAMPLERS = {
 DENSITIES = {"cfg5a-pdf": ("pdf", False), "cfg5a-logpdf": ("pdf", True), "cfg5a-cdf": ("cdf", False),
              "cfg5a-logcdf": ("cdf", True)}
 # kernel kind (polyagamma_b200._lib.KERNEL_KINDS) -> kernel name
-KERNEL_NAMES = {"tile": "tile_kernel (classify + in-tile normal / left-saddle / devroye + list compaction)",
+KERNEL_NAMES = {"tile": "tile_kernel (classify + in-tile normal / left-saddle + list compaction)",
                 "small": "small_kernel", "devroye": "sample_kernel<DevroyeT<pair|MSH>>",
                 "alternate": "sample_kernel<Alternate>", "alternate_left": "sample_kernel<AlternateLeft, fused setup>",
                 "saddle": "sample_kernel<SaddleFull>", "saddle_left": "sample_kernel<SaddleLeft>",

@@ -65,9 +65,9 @@ int launch_test_math(int which, const double* d_in, size_t n, double* d_out, cud
 enum : int {
     kKindDrain = 0,     // every divergent bucket of a mid-size fill in one launch
     kKindSmall = 1,     // the one-launch kernel for small fills
-    kKindTile = 2,      // tile kernel: classify + in-tile normal / far saddle / devroye + list compaction
-    // sampling kernels: + 0 devroye, 1 alternate, 2 saddle, 3 saddle-left, 4 saddle-far, 5 alternate-left,
-    // 6 saddle-mid
+    kKindTile = 2,      // tile kernel: classify + in-tile normal / left-only saddle + list compaction
+    // sampling kernels: + 0 devroye, 1 alternate, 2 saddle (full), 3 saddle-left (identity range only), 4 unused,
+    // 5 alternate-left, 6 unused
     kKindDevroye = 3,
     kKindNormal = 10,
     kKindGamma = 11,

@@ -1,13 +1,18 @@
 // pgm_sampler.cu -- the batched Polya-Gamma fill on sm_100a.
 //
 // Replaces src/pgm_random.c:144-180 (pgm_random_polyagamma / _fill / _fill2 and the hybrid
-// dispatch).  Pipeline for one chunk of the output index range:
+// dispatch).  One pass (up to 2^27 elements) of the output index range:
 //
-//   hybrid:   bucket_kernel     one pass: bucket id per element (+ NaN/inf for invalid h), one list
-//                               reservation per bucket and block, per-bucket element lists
-//             per bucket        setup_kernel<M> (per-element records) + sample_kernel<M>, or
-//                               dense_kernel, over that bucket's list
-//   explicit: the same kernels over the identity list
+//   tile_kernel      persistent blocks, tiles of 2048 elements: load (h, z) once, classify (hybrid rule or the
+//                    explicit method), draw the convergent buckets in place -- normal approximation and left-only
+//                    saddle, from shared memory -- and append the others as compact (index, h, z) records to
+//                    per-bucket lists; the tile's outputs leave as coalesced 16-byte stores
+//   per list         setup_kernel<M> (per-element records; alternate and full saddle only) and sample_kernel<M>
+//                    on two helper streams, overlapping the next pass's tile_kernel
+//   small fills      small_kernel (one launch, one thread per element) up to 2^17 elements, tile_kernel +
+//                    drain_kernel (every list in one launch) up to 2^18
+//   scalar (h, z)    one record for the whole call, the method's kernels over the identity range
+//   gamma            dense_kernel<gamma> over the identity range
 //
 // sample_kernel: every lane owns one element at a time and advances it by ONE proposal
 // attempt per loop trip (pgm_methods.cuh); lanes whose element completed are retired and
