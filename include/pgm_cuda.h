@@ -182,7 +182,7 @@ uint64_t pgm_cuda_launch_count(void);
  * events and returns, per kernel kind, the summed milliseconds and the launch count.
  * Kinds: 0 the drain kernel (every divergent bucket of a mid-size fill in one launch), 1 the one-launch
  * kernel of small fills, 2 the tile
- * kernel (classification, the in-tile normal / left-saddle / devroye draws, list compaction);
+ * kernel (classification, the in-tile normal / left-saddle draws, list compaction);
  * sampling kernels over a list or an identity range: 3 devroye (both proposal variants), 4 alternate,
  * 5 saddle (both envelope pieces), 6 saddle-left (left piece only), 7 unused, 8 alternate-left (left
  * piece only, |z| >= 14), 9 unused; 10 normal, 11 gamma, 12 density; per-element setup kernels 13..19 in
