@@ -605,10 +605,15 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
 
         // ---- 2. group offsets (every warp works them out for itself: identical values, no barrier); clear the
         // other set of counters for the next tile; write the local lists ----
-        if (lane < kNumBuckets) {
-            uint32_t off = 0;
-            for (uint32_t q = 0; q < lane; ++q) off += cnt[q];
-            S.off[lane] = off;
+        {
+            const uint32_t c = (lane < kNumBuckets) ? cnt[lane] : 0u;
+            uint32_t incl = c;  // inclusive scan over the first eight lanes
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if ((int)lane >= d) incl += t;
+            }
+            if (lane < kNumBuckets) S.off[lane] = incl - c;
             if (tid < kNumBuckets) {
                 S.cnt2[parity ^ 1u][tid] = 0;
                 S.next2[parity ^ 1u][tid] = 0;
@@ -673,23 +678,37 @@ tile_kernel(FillArgs a, uint32_t n, int method, uint32_t* __restrict__ ctl, Elem
             S.gbase[tid] = reserved;
         }
         {
-            // normal approximation: work queue of batches of 64 elements
+            // normal approximation: a work queue of items of 64 elements (two per lane, interleaved), and of 32
+            // elements for the last block-load of them, so that the warps reach the barrier below closer together
             const uint32_t cn = cnt[kBNormal];
             const uint16_t* ln = S.list + S.off[kBNormal];
-            const uint32_t nitems = (cn + 63u) >> 6;
+            const uint32_t nfull = cn > (uint32_t)kTileThreads ? (cn - (uint32_t)kTileThreads) >> 6 : 0u;
+            const uint32_t rest0 = nfull << 6;
+            const uint32_t nitems = nfull + ((cn - rest0 + 31u) >> 5);
             for (;;) {
                 uint32_t it = 0;
                 if (lane == 0) it = atomicAdd(&next[kBNormal], 1u);
                 it = __shfl_sync(0xffffffffu, it, 0);
                 if (it >= nitems) break;
-                const uint32_t i = (it << 6) + lane;
-                if (i < cn) {
-                    const bool two = i + 32u < cn;
-                    const uint32_t e0 = ln[i], e1 = two ? ln[i + 32u] : e0;
+                if (it < nfull) {
+                    const uint32_t i = (it << 6) + lane;
+                    const uint32_t e0 = ln[i], e1 = ln[i + 32u];
                     const double2 v = normal_pair(S.hout[e0], S.z[e0], S.hout[e1], S.z[e1], a.key.k0, a.key.k1,
                                                   index0 + e0, index0 + e1);
-                    if (two) S.hout[e1] = v.y;
+                    S.hout[e1] = v.y;
                     S.hout[e0] = v.x;
+                }
+                else {
+                    const uint32_t i = rest0 + ((it - nfull) << 5) + lane;
+                    if (i < cn) {
+                        const uint32_t e0 = ln[i];
+                        PhiloxKey key;
+                        key.k0 = a.key.k0;
+                        key.k1 = a.key.k1;
+                        RngInline r0;
+                        r0.init(key, index0 + e0);
+                        S.hout[e0] = normal_approx_sample(r0, S.hout[e0], S.z[e0]);
+                    }
                 }
             }
         }
