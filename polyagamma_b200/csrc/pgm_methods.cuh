@@ -728,7 +728,10 @@ table_interp(const double* tab, double zz)
 // above it (x >= 8: a right-piece proposal far in the tail) the direct solve runs.
 // Every lane of a warp therefore takes the same dozen instructions per proposal instead of one to four
 // tanh / tan evaluations: the far / mid / left split of the saddle buckets (round 1) is gone.
-constexpr int kTabBits = 7;
+#ifndef PGM_SADDLE_TAB_BITS
+#define PGM_SADDLE_TAB_BITS 7
+#endif
+constexpr int kTabBits = PGM_SADDLE_TAB_BITS;
 constexpr int kTabEmin = -5, kTabEmax = 3;
 constexpr int kTabCells = (kTabEmax - kTabEmin) << kTabBits;
 static __device__ double2 g_saddle_tab[4 * kTabCells];  // per cell: cubic in t of Gr (c0 c1 | c2 c3), then of Hr
