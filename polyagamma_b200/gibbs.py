@@ -20,7 +20,8 @@ def logistic_omega_step(X, beta, n_trials=1.0, *, random_state=None, method=None
                         return_omega=True, return_psi=False, first_index=0):
     """``psi = X @ beta``; ``omega ~ PG(n_trials, psi)``; ``G = X.T @ diag(omega) @ X``.
 
-    X: (n, p) float64 CUDA tensor, row-major (``stride(1) == 1``), ``p <= 64``; beta: (p,);
+    X: (n, p) float64 CUDA tensor, row-major (``stride(1) == 1``); beta: (p,).  ``p <= 64`` runs the fused
+    kernels (one C-ABI call); wider X falls back to two cuBLAS GEMMs around the same draw.
     n_trials: scalar or (n,) tensor of shape parameters.  Returns ``(G, omega)`` (``omega`` is None
     when ``return_omega=False``), plus ``psi`` when ``return_psi=True``.  All outputs are CUDA tensors.
     """
@@ -30,9 +31,12 @@ def logistic_omega_step(X, beta, n_trials=1.0, *, random_state=None, method=None
     if X.stride(1) != 1 and X.shape[1] > 1:
         X = X.contiguous()
     n, p = X.shape
-    if not 1 <= p <= 64:
-        raise ValueError("logistic_omega_step supports 1 <= p <= 64 columns")
+    if p < 1:
+        raise ValueError("logistic_omega_step needs at least one column")
     dev = _device_of(X)
+    if p > 64:
+        return _wide_omega_step(X, beta, n_trials, random_state, method, ref_compat, return_omega, return_psi,
+                                first_index, dev)
     beta = torch.as_tensor(beta, dtype=torch.float64, device=dev).contiguous()
     if beta.shape != (p,):
         raise ValueError(f"beta must have shape ({p},)")
@@ -57,6 +61,31 @@ def logistic_omega_step(X, beta, n_trials=1.0, *, random_state=None, method=None
             ctypes.c_void_p(psi.data_ptr()) if psi is not None else None, int(first_index), _stream_ptr(dev))
     _lib.check(rc, "pgm_cuda_logistic_omega_step")
     return (gram, omega, psi) if return_psi else (gram, omega)
+
+
+def _wide_omega_step(X, beta, n_trials, random_state, method, ref_compat, return_omega, return_psi, first_index, dev):
+    """p > 64: the fused kernels hold the upper triangle of G in registers (72 accumulators per lane at p = 64)
+    and do not go wider.  psi and G become two library GEMMs (cuBLAS FP64 through torch); the draw in between
+    is the same call, with the same streams, as for narrow X."""
+    from ._api import random_polyagamma
+
+    torch = _torch()
+    beta = torch.as_tensor(beta, dtype=torch.float64, device=dev).contiguous()
+    if beta.shape != (X.shape[1],):
+        raise ValueError(f"beta must have shape ({X.shape[1]},)")
+    psi = X @ beta
+    if isinstance(n_trials, (int, float)):
+        nt = float(n_trials)
+    else:
+        nt = torch.as_tensor(n_trials, dtype=torch.float64, device=dev).contiguous()
+        if nt.shape != (X.shape[0],):
+            raise ValueError(f"n_trials must be a scalar or have shape ({X.shape[0]},)")
+    omega = random_polyagamma(nt, psi, method=method, random_state=random_state, disable_checks=True,
+                              ref_compat=ref_compat, first_index=int(first_index))
+    gram = X.T @ (omega[:, None] * X)
+    gram = 0.5 * (gram + gram.T)  # (exactly symmetric, like the fused kernel's result)
+    out = (gram, omega if return_omega else None)
+    return out + (psi,) if return_psi else out
 
 
 def allreduce_gram(gram, group=None):

@@ -77,7 +77,30 @@ def test_omega_step_equals_random_polyagamma(torch):
     G4, om4 = logistic_omega_step(wide[:, :p].contiguous(), beta, 1.0, random_state=(9, 9))
     assert torch.equal(om3, om4) and torch.equal(G3, G4)
     with pytest.raises(ValueError):
-        logistic_omega_step(torch.zeros(4, 65, device="cuda", dtype=torch.float64), torch.zeros(65))
+        logistic_omega_step(torch.zeros(4, 0, device="cuda", dtype=torch.float64), torch.zeros(0))
+
+
+def test_wide_design_matrix_falls_back_to_library_gemms(torch):
+    """p > 64: psi and the Gram matrix come from cuBLAS, the draw is the same call with the same streams."""
+    import polyagamma_b200 as pg
+    from polyagamma_b200.gibbs import logistic_omega_step
+
+    g = torch.Generator(device="cuda")
+    g.manual_seed(8)
+    n, p = 50_003, 100
+    X = torch.randn(n, p, device="cuda", dtype=torch.float64, generator=g)
+    beta = torch.randn(p, device="cuda", dtype=torch.float64, generator=g) * 0.2
+    G, om, psi = logistic_omega_step(X, beta, 2.0, random_state=(4, 4), return_psi=True)
+    assert torch.equal(om, pg.random_polyagamma(2.0, psi, random_state=(4, 4), disable_checks=True))
+    want = X.T @ (om[:, None] * X)
+    assert float((G - want).abs().max() / want.abs().max()) < 1e-13
+    assert torch.equal(G, G.T) and G.shape == (p, p)
+    # the first 64 columns through the fused kernels give the same omegas for the same psi
+    b64 = torch.zeros(p, device="cuda", dtype=torch.float64)
+    b64[:64] = beta[:64]
+    _, om_wide = logistic_omega_step(X, b64, 2.0, random_state=(4, 5))
+    _, om_fused = logistic_omega_step(X[:, :64], beta[:64], 2.0, random_state=(4, 5))
+    assert float((om_wide - om_fused).abs().max()) < 1e-9  # (psi differs in the last bits between the two GEMVs)
 
 
 @pytest.mark.parametrize("world", [2, 3])
