@@ -114,7 +114,56 @@ class ClockSampler:
         self.lines = []
         self.thread = None
 
+    def _nvml_handle(self):
+        """NVML handle of this rank's GPU (by the UUID torch reports: CUDA_VISIBLE_DEVICES may renumber), or None."""
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.gpu).uuid)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except TypeError:
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            return pynvml, h
+        except Exception:
+            return None
+
+    def _poll_nvml(self, pynvml, h):
+        names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        try:
+            smax = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            smax = None
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = int(get_reasons(h))
+                try:
+                    power = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    power = None
+                self.nvml_samples.append((sm, smax, power, [k for k, bit in names.items() if mask & bit]))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.004)
+
     def start(self):
+        self.nvml_samples = []
+        self.stop_flag = threading.Event()
+        got = self._nvml_handle()
+        if got is not None:
+            self.thread = threading.Thread(target=self._poll_nvml, args=got, daemon=True)
+            self.thread.start()
+            self.mode = "nvml"
+            return
+        self.mode = "nvidia-smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE,
@@ -130,6 +179,16 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if getattr(self, "mode", "") == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            sm = [x[0] for x in self.nvml_samples]
+            smax = [x[1] for x in self.nvml_samples if x[1] is not None]
+            power = [x[2] for x in self.nvml_samples if x[2] is not None]
+            reasons = sorted({r for x in self.nvml_samples for r in x[3]})
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                    "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": reasons,
+                    "source": "NVML, polled every 4 ms during the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
