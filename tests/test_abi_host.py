@@ -181,3 +181,14 @@ def test_argument_checks_need_no_gpu():
     assert L.pgm_cuda_polyagamma_density_strided(8, one, one, one, 0, shape, st, st, st, one, None) == _lib.EINVAL
     neg = (i64 * 1)(-3)
     assert L.pgm_cuda_random_polyagamma_fill2_strided(1, 0, one, one, _lib.HYBRID, 1, neg, st, st, one, 0, None) == _lib.EINVAL
+    # host-pointer entry points: NULL arrays, bad strides, duplicate devices; an empty call is a no-op
+    assert L.pgm_cuda_download(None, one, 5, None) == _lib.EINVAL
+    assert L.pgm_cuda_download(one, None, 5, None) == _lib.EINVAL
+    assert L.pgm_cuda_download(None, None, 0, None) == 0
+    assert L.pgm_cuda_random_polyagamma_fill2_host(1, 0, None, 1, one, 1, _lib.HYBRID, 4, one, 0, 0) == _lib.EINVAL
+    assert L.pgm_cuda_random_polyagamma_fill2_host(1, 0, one, 2, one, 1, _lib.HYBRID, 4, one, 0, 0) == _lib.EINVAL
+    assert L.pgm_cuda_random_polyagamma_fill2_host(1, 0, one, 1, one, 1, _lib.HYBRID, 0, None, 0, 0) == 0
+    devs = (ctypes.c_int * 2)(0, 0)
+    assert L.pgm_cuda_random_polyagamma_fill2_host_multi(1, 0, one, 1, one, 1, _lib.HYBRID, 4, one, 0, devs, 2) == _lib.EINVAL
+    assert L.pgm_cuda_polyagamma_density_host(0, None, 1, one, 1, one, 1, 3, one, -1) == _lib.EINVAL
+    assert L.pgm_cuda_polyagamma_density_host(9, one, 1, one, 1, one, 1, 3, one, -1) == _lib.EINVAL
